@@ -1,0 +1,547 @@
+// Collective kernels for sm_100a: bucketed all-reduce (one-shot / two-shot over peer-mapped
+// arenas), bucketed broadcast, local unpack and a device barrier.
+//
+// Replaces the per-tensor NCCL all-reduce + per-tensor divide loop of the reference
+// (flashy/distrib.py:105-111, :122-127, :174-190).  The path is an elementwise reduction: it
+// is bound by NVLink (W > 1 GPUs) or HBM (virtual ranks on one GPU), never by the tensor
+// cores, so there is no tcgen05 here -- only 128-bit coalesced global/peer accesses, release /
+// acquire flags at system scope, and fp32 accumulation in registers.
+//
+// Data flow of the two-shot kernel, for hosted rank r and CTA b (every CTA owns slice b of
+// every shard, on every rank, so CTA b only ever needs to synchronise with the CTAs b of the
+// other ranks):
+//   pack      grads (any addresses) -> own arena, slice b of each of the W shards  [+ cast]
+//   barrier   flags[b][r] <- epoch on every peer (st.release.sys), wait for all W flags
+//   reduce    slice b of shard r: sum the W arenas in rank order (fp32), /W, store to own arena
+//   barrier
+//   gather    slice b of shard s from arena s, for all s -> output tensors      [+ cast]
+// The staging region alternates between two halves on successive calls of a plan, which is
+// what makes a third (end-of-kernel) barrier unnecessary.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "fx_internal.h"
+
+namespace {
+
+// ============================================================================ primitives
+__device__ __forceinline__ uint4 ld16(const void* p) {
+    uint4 v;
+    asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st16(void* p, const uint4& v) {
+    asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__device__ __forceinline__ FxPad* pad_of(char* arena) { return reinterpret_cast<FxPad*>(arena); }
+
+// All CTAs `b` of the W ranks meet here.  `target` is the new epoch value.
+__device__ __forceinline__ void block_barrier(const FxLaunch& a, int rank, int world, int b,
+                                              uint32_t target) {
+    __syncthreads();
+    if (threadIdx.x < world) {
+        const int q = threadIdx.x;
+        __threadfence_system();
+        st_release_sys(&pad_of(a.arena[q])->flags[b][rank], target);
+        const uint32_t* mine = &pad_of(a.arena[rank])->flags[b][q];
+        unsigned long long t0 = 0;
+        uint32_t spins = 0;
+        while ((int32_t)(ld_acquire_sys(mine) - target) < 0) {
+            if ((++spins & 0x3ff) == 0) {
+                const unsigned long long now = globaltimer_ns();
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > a.timeout_ns) {        // peer never arrived: flag it, do not hang
+                    *reinterpret_cast<volatile uint32_t*>(a.status) = (uint32_t)(-FX_ERR_TIMEOUT);
+                    __threadfence_system();
+                    break;
+                }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// ============================================================================ type traits
+template <typename T> struct Acc { using type = float; };
+template <> struct Acc<double> { using type = double; };
+template <> struct Acc<int32_t> { using type = int32_t; };
+template <> struct Acc<int64_t> { using type = int64_t; };
+template <> struct Acc<uint8_t> { using type = uint8_t; };
+
+template <typename D, typename S> __device__ __forceinline__ D cvt(S x) { return static_cast<D>(x); }
+template <> __device__ __forceinline__ float cvt<float, __nv_bfloat16>(__nv_bfloat16 x) { return __bfloat162float(x); }
+template <> __device__ __forceinline__ __nv_bfloat16 cvt<__nv_bfloat16, float>(float x) { return __float2bfloat16_rn(x); }
+template <> __device__ __forceinline__ float cvt<float, __half>(__half x) { return __half2float(x); }
+template <> __device__ __forceinline__ __half cvt<__half, float>(float x) { return __float2half_rn(x); }
+template <> __device__ __forceinline__ __nv_bfloat16 cvt<__nv_bfloat16, __nv_bfloat16>(__nv_bfloat16 x) { return x; }
+template <> __device__ __forceinline__ __half cvt<__half, __half>(__half x) { return x; }
+
+template <typename T> union Vec16 {
+    uint4 u;
+    T e[FX_VEC_BYTES / sizeof(T)];
+    __device__ Vec16() {}
+};
+
+template <int OP, typename A> __device__ __forceinline__ A combine(A x, A y) {
+    if (OP == FX_MAX) return x > y ? x : y;
+    if (OP == FX_MIN) return x < y ? x : y;
+    if (OP == FX_PROD) return x * y;
+    return x + y;
+}
+
+// ============================================================================ bucket <-> tensors
+// Largest i with off[i] <= x (off is sorted, n >= 1, off[0] == 0).
+__device__ __forceinline__ int find_tensor(const long long* off, int n, long long x) {
+    int lo = 0, hi = n;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (off[mid] <= x) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// Block-wide converting copy of `len` elements.  The vector path needs both ends 16-byte
+// aligned (always true for the arena side; torch allocations make it true for the tensors in
+// practice); otherwise the whole range goes element by element.
+template <typename Src, typename Dst>
+__device__ __forceinline__ void copy_convert(const Src* __restrict__ src, Dst* __restrict__ dst, long long len) {
+    constexpr int kMin = sizeof(Src) < sizeof(Dst) ? sizeof(Src) : sizeof(Dst);
+    constexpr int UE = FX_VEC_BYTES / kMin;                    // elements per unit
+    constexpr int NL = UE * sizeof(Src) / FX_VEC_BYTES;        // 16-byte loads per unit
+    constexpr int NS = UE * sizeof(Dst) / FX_VEC_BYTES;        // 16-byte stores per unit
+    constexpr int U = NL >= 2 ? 2 : 4;                         // units in flight per thread
+    const bool aligned = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0;
+    const long long nunit = aligned ? len / UE : 0;
+    for (long long u0 = threadIdx.x; u0 < nunit; u0 += (long long)U * FX_THREADS) {
+        Vec16<Src> in[U][NL];
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            const long long u = u0 + (long long)k * FX_THREADS;
+            if (u < nunit) {
+#pragma unroll
+                for (int j = 0; j < NL; ++j)
+                    in[k][j].u = ld16(reinterpret_cast<const uint4*>(src + u * UE) + j);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            const long long u = u0 + (long long)k * FX_THREADS;
+            if (u < nunit) {
+                Vec16<Dst> out[NS];
+#pragma unroll
+                for (int e = 0; e < UE; ++e) {
+                    constexpr int SPL = FX_VEC_BYTES / sizeof(Src), DPL = FX_VEC_BYTES / sizeof(Dst);
+                    out[e / DPL].e[e % DPL] = cvt<Dst, Src>(in[k][e / SPL].e[e % SPL]);
+                }
+#pragma unroll
+                for (int j = 0; j < NS; ++j)
+                    st16(reinterpret_cast<uint4*>(dst + u * UE) + j, out[j].u);
+            }
+        }
+    }
+    for (long long e = nunit * UE + threadIdx.x; e < len; e += FX_THREADS)
+        dst[e] = cvt<Dst, Src>(src[e]);
+}
+
+// Calls f(i, s0, s1) for every tensor i overlapping bucket range [lo, hi): elements
+// [s0, s1) of the bucket belong to tensor i starting at tensor element s0 - off[i].
+template <typename F>
+__device__ __forceinline__ void for_each_segment(const FxLaunch& a, long long lo, long long hi, F f) {
+    const long long* off = a.off;
+    const long long* numel = a.off + a.n + 1;
+    if (lo >= off[a.n]) return;                   // pure padding
+    for (int i = find_tensor(off, a.n, lo); i < a.n; ++i) {
+        const long long t0 = off[i];
+        if (t0 >= hi) break;
+        const long long s0 = lo > t0 ? lo : t0;
+        const long long t1 = t0 + numel[i];
+        const long long s1 = hi < t1 ? hi : t1;
+        if (s1 > s0) f(i, s0, s1);
+    }
+}
+
+template <typename T, typename S>
+__device__ __forceinline__ void pack_range(const FxLaunch& a, int l, T* stage, long long lo, long long hi) {
+    for_each_segment(a, lo, hi, [&](int i, long long s0, long long s1) {
+        const S* src = static_cast<const S*>(a.in_ptrs[(long long)l * a.n + i]) + (s0 - a.off[i]);
+        copy_convert<S, T>(src, stage + s0, s1 - s0);
+    });
+}
+
+template <typename T, typename S>
+__device__ __forceinline__ void unpack_range(const FxLaunch& a, int l, const T* stage, long long lo, long long hi) {
+    for_each_segment(a, lo, hi, [&](int i, long long s0, long long s1) {
+        S* dst = static_cast<S*>(a.out_ptrs[(long long)l * a.n + i]) + (s0 - a.off[i]);
+        copy_convert<T, S>(stage + s0, dst, s1 - s0);
+    });
+}
+
+// ============================================================================ reductions
+template <typename T, int OP>
+__device__ __forceinline__ void accumulate(typename Acc<T>::type* acc, const uint4& raw, bool first) {
+    using A = typename Acc<T>::type;
+    constexpr int VEC = FX_VEC_BYTES / sizeof(T);
+    Vec16<T> v;
+    v.u = raw;
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+        const A x = cvt<A, T>(v.e[e]);
+        acc[e] = first ? x : combine<OP, A>(acc[e], x);
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ uint4 finalize(typename Acc<T>::type* acc, bool avg, int world) {
+    using A = typename Acc<T>::type;
+    constexpr int VEC = FX_VEC_BYTES / sizeof(T);
+    Vec16<T> v;
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+        A x = acc[e];
+        if (avg) x = x / static_cast<A>(world);           // true division, flashy/distrib.py:111
+        v.e[e] = cvt<T, A>(x);
+    }
+    return v.u;
+}
+
+// Reduce `nvec` 16-byte vectors starting at byte offset `byte_off` of every rank's arena, in
+// rank order, and store the result at the same offset of `dst_arena`.  W > 0: compile-time
+// world (all W loads of a vector in flight at once); W == 0: runtime world.
+template <typename T, int W, int OP>
+__device__ __forceinline__ void reduce_vectors(const FxLaunch& a, int world, unsigned long long byte_off,
+                                               long long nvec, bool avg, char* dst_arena) {
+    using A = typename Acc<T>::type;
+    constexpr int VEC = FX_VEC_BYTES / sizeof(T);
+    uint4* dst = reinterpret_cast<uint4*>(dst_arena + byte_off);
+    if (W > 0) {
+        constexpr int WW = W > 0 ? W : 1;
+        constexpr int U = (16 / WW) < 1 ? 1 : ((16 / WW) > 4 ? 4 : (16 / WW));
+        const uint4* base[WW];
+#pragma unroll
+        for (int q = 0; q < WW; ++q) base[q] = reinterpret_cast<const uint4*>(a.arena[q] + byte_off);
+        for (long long v0 = threadIdx.x; v0 < nvec; v0 += (long long)U * FX_THREADS) {
+            uint4 raw[U][WW];
+#pragma unroll
+            for (int k = 0; k < U; ++k) {
+                const long long v = v0 + (long long)k * FX_THREADS;
+                if (v < nvec) {
+#pragma unroll
+                    for (int q = 0; q < WW; ++q) raw[k][q] = ld16(base[q] + v);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < U; ++k) {
+                const long long v = v0 + (long long)k * FX_THREADS;
+                if (v < nvec) {
+                    A acc[VEC];
+#pragma unroll
+                    for (int q = 0; q < WW; ++q) accumulate<T, OP>(acc, raw[k][q], q == 0);
+                    st16(dst + v, finalize<T>(acc, avg, world));
+                }
+            }
+        }
+    } else {
+        constexpr int U = 4;
+        for (long long v0 = threadIdx.x; v0 < nvec; v0 += (long long)U * FX_THREADS) {
+            A acc[U][VEC];
+            for (int q = 0; q < world; ++q) {
+                const uint4* base = reinterpret_cast<const uint4*>(a.arena[q] + byte_off);
+                uint4 raw[U];
+#pragma unroll
+                for (int k = 0; k < U; ++k) {
+                    const long long v = v0 + (long long)k * FX_THREADS;
+                    if (v < nvec) raw[k] = ld16(base + v);
+                }
+#pragma unroll
+                for (int k = 0; k < U; ++k) {
+                    const long long v = v0 + (long long)k * FX_THREADS;
+                    if (v < nvec) accumulate<T, OP>(acc[k], raw[k], q == 0);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < U; ++k) {
+                const long long v = v0 + (long long)k * FX_THREADS;
+                if (v < nvec) st16(dst + v, finalize<T>(acc[k], avg, world));
+            }
+        }
+    }
+}
+
+// One-shot tail: reduce bucket range [lo, hi) over all arenas and write the result straight
+// into the output tensors (no second staging pass, no second barrier).
+template <typename T, typename S, int OP>
+__device__ __forceinline__ void reduce_unpack_range(const FxLaunch& a, int world, int l, unsigned long long region,
+                                                    long long lo, long long hi, bool avg) {
+    using A = typename Acc<T>::type;
+    constexpr int VEC = FX_VEC_BYTES / sizeof(T);
+    for_each_segment(a, lo, hi, [&](int i, long long s0, long long s1) {
+        S* dst = static_cast<S*>(a.out_ptrs[(long long)l * a.n + i]) + (s0 - a.off[i]);
+        const long long len = s1 - s0;
+        const long long nvec = (len + VEC - 1) / VEC;     // the last vector may run into padding
+        for (long long v = threadIdx.x; v < nvec; v += FX_THREADS) {
+            A acc[VEC];
+            for (int q = 0; q < world; ++q) {
+                const uint4* base = reinterpret_cast<const uint4*>(a.arena[q] + region) ;
+                accumulate<T, OP>(acc, ld16(reinterpret_cast<const char*>(base) + (s0 + v * VEC) * sizeof(T)), q == 0);
+            }
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+                const long long idx = v * VEC + e;
+                if (idx < len) {
+                    A x = acc[e];
+                    if (avg) x = x / static_cast<A>(world);
+                    dst[idx] = cvt<S, T>(cvt<T, A>(x));      // round to the wire type first: same bits as two-shot
+                }
+            }
+        }
+    });
+}
+
+// ============================================================================ kernels
+__device__ __forceinline__ void finish_launch(FxPlanState* st, FxPad* pad, int b, uint32_t epoch, uint32_t calls) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        pad->block_epoch[b] = epoch;
+        __threadfence();
+        if (atomicAdd(&st->finished, 1u) == gridDim.x - 1) {    // last CTA of this hosted rank
+            st->finished = 0;
+            __threadfence();
+            *reinterpret_cast<volatile uint32_t*>(&st->calls) = calls + 1;
+        }
+    }
+}
+
+template <typename T, typename S, int W, int OP>
+__global__ void __launch_bounds__(FX_THREADS, 1) k_two_shot(const FxLaunch a) {
+    const int l = blockIdx.y, b = blockIdx.x;
+    const int rank = a.rank0 + l;
+    const int world = W > 0 ? W : a.world;
+    FxPlanState* st = a.state + l;
+    const uint32_t calls = ld_volatile_u32(&st->calls);
+    const unsigned long long region = a.region[calls & 1];
+    char* my = a.arena[rank];
+    T* stage = reinterpret_cast<T*>(my + region);
+    uint32_t epoch = pad_of(my)->block_epoch[b];
+    const long long slice = a.slice_elems, shard = a.shard_elems;
+    const bool avg = a.op == FX_AVG;
+
+    for (int s = 0; s < world; ++s) {
+        const long long lo = s * shard + b * slice;
+        pack_range<T, S>(a, l, stage, lo, lo + slice);
+    }
+    block_barrier(a, rank, world, b, ++epoch);
+
+    {
+        const long long lo = rank * shard + b * slice;
+        reduce_vectors<T, W, OP>(a, world, region + (unsigned long long)lo * sizeof(T),
+                                 slice / (FX_VEC_BYTES / (long long)sizeof(T)), avg, my);
+    }
+    block_barrier(a, rank, world, b, ++epoch);
+
+    for (int j = 0; j < world; ++j) {
+        const int s = (rank + j) % world;                     // stagger the peers
+        const long long lo = s * shard + b * slice;
+        const T* from = reinterpret_cast<const T*>(a.arena[s] + region);
+        if (a.mode == FX_MODE_FUSED) {
+            unpack_range<T, S>(a, l, from, lo, lo + slice);
+        } else if (s != rank) {
+            copy_convert<T, T>(from + lo, stage + lo, slice);
+        }
+    }
+    finish_launch(st, pad_of(my), b, epoch, calls);
+}
+
+template <typename T, typename S, int OP>
+__global__ void __launch_bounds__(FX_THREADS, 1) k_one_shot(const FxLaunch a) {
+    const int l = blockIdx.y, b = blockIdx.x;
+    const int rank = a.rank0 + l;
+    const int world = a.world;
+    FxPlanState* st = a.state + l;
+    const uint32_t calls = ld_volatile_u32(&st->calls);
+    const unsigned long long region = a.region[calls & 1];
+    char* my = a.arena[rank];
+    uint32_t epoch = pad_of(my)->block_epoch[b];
+    const long long lo = b * a.slice_elems, hi = lo + a.slice_elems;
+    pack_range<T, S>(a, l, reinterpret_cast<T*>(my + region), lo, hi);
+    block_barrier(a, rank, world, b, ++epoch);
+    reduce_unpack_range<T, S, OP>(a, world, l, region, lo, hi, a.op == FX_AVG);
+    finish_launch(st, pad_of(my), b, epoch, calls);
+}
+
+// Bit copy from rank `src`: the source packs, everyone else pulls from the source's arena.
+__global__ void __launch_bounds__(FX_THREADS, 1) k_broadcast(const FxLaunch a) {
+    const int l = blockIdx.y, b = blockIdx.x;
+    const int rank = a.rank0 + l;
+    const int world = a.world;
+    FxPlanState* st = a.state + l;
+    const uint32_t calls = ld_volatile_u32(&st->calls);
+    const unsigned long long region = a.region[calls & 1];
+    char* my = a.arena[rank];
+    uint32_t epoch = pad_of(my)->block_epoch[b];
+    const long long slice = a.slice_elems, shard = a.shard_elems;
+    if (rank == a.src) {
+        for (int s = 0; s < world; ++s) {
+            const long long lo = s * shard + b * slice;
+            pack_range<uint8_t, uint8_t>(a, l, reinterpret_cast<uint8_t*>(my + region), lo, lo + slice);
+        }
+    }
+    block_barrier(a, rank, world, b, ++epoch);
+    if (rank != a.src) {
+        const uint8_t* from = reinterpret_cast<const uint8_t*>(a.arena[a.src] + region);
+        for (int j = 0; j < world; ++j) {
+            const int s = (rank + j) % world;                 // spread the readers over the source's memory
+            const long long lo = s * shard + b * slice;
+            unpack_range<uint8_t, uint8_t>(a, l, from, lo, lo + slice);
+        }
+    }
+    finish_launch(st, pad_of(my), b, epoch, calls);
+}
+
+// Second half of the eager path: local arena -> output tensors (flashy/distrib.py:187-190).
+template <typename T, typename S>
+__global__ void __launch_bounds__(FX_THREADS, 1) k_unpack(const FxLaunch a) {
+    const int l = blockIdx.y, b = blockIdx.x;
+    const int rank = a.rank0 + l;
+    const uint32_t calls = ld_volatile_u32(&a.state[l].calls);
+    const unsigned long long region = a.region[(calls - 1) & 1];     // the region the matching BEGIN used
+    const T* stage = reinterpret_cast<const T*>(a.arena[rank] + region);
+    for (int s = 0; s < a.world; ++s) {
+        const long long lo = s * a.shard_elems + b * a.slice_elems;
+        unpack_range<T, S>(a, l, stage, lo, lo + a.slice_elems);
+    }
+}
+
+__global__ void __launch_bounds__(FX_THREADS, 1) k_barrier(const FxLaunch a) {
+    const int rank = a.rank0 + blockIdx.y;
+    FxPad* pad = pad_of(a.arena[rank]);
+    uint32_t epoch = pad->block_epoch[0];
+    block_barrier(a, rank, a.world, 0, ++epoch);
+    if (threadIdx.x == 0) pad->block_epoch[0] = epoch;
+}
+
+// ============================================================================ dispatch
+template <typename K>
+int launch(K kernel, const fx_plan* plan, int grid_x, const FxLaunch& args, cudaStream_t stream) {
+    const fx_comm* c = plan ? plan->comm : nullptr;
+    const int n_local = args.n_local;
+    dim3 grid(grid_x, n_local), block(FX_THREADS);
+    void* params[] = {const_cast<FxLaunch*>(&args)};
+    cudaError_t e;
+    if (n_local > 1) {
+        // virtual ranks spin on each other's flags: all their CTAs must be co-resident
+        e = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kernel), grid, block, params, 0, stream);
+    } else {
+        e = cudaLaunchKernel(reinterpret_cast<const void*>(kernel), grid, block, params, 0, stream);
+    }
+    (void)c;
+    if (e != cudaSuccess) return fx_fail(FX_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+    return FX_OK;
+}
+
+template <typename T, typename S, int OP>
+int launch_allreduce_w(fx_plan* plan, const FxLaunch& a, cudaStream_t s) {
+    if (plan->algo == FX_ALGO_ONE_SHOT) return launch(k_one_shot<T, S, OP>, plan, plan->grid_x, a, s);
+    if (OP == FX_SUM) {
+        switch (a.world) {
+            case 2: return launch(k_two_shot<T, S, 2, OP>, plan, plan->grid_x, a, s);
+            case 4: return launch(k_two_shot<T, S, 4, OP>, plan, plan->grid_x, a, s);
+            case 8: return launch(k_two_shot<T, S, 8, OP>, plan, plan->grid_x, a, s);
+            default: break;
+        }
+    }
+    return launch(k_two_shot<T, S, 0, OP>, plan, plan->grid_x, a, s);
+}
+
+template <typename T, typename S>
+int launch_allreduce_op(fx_plan* plan, const FxLaunch& a, cudaStream_t s) {
+    switch (a.op) {
+        case FX_SUM: case FX_AVG: return launch_allreduce_w<T, S, FX_SUM>(plan, a, s);
+        case FX_MAX: return launch_allreduce_w<T, S, FX_MAX>(plan, a, s);
+        case FX_MIN: return launch_allreduce_w<T, S, FX_MIN>(plan, a, s);
+        case FX_PROD: return launch_allreduce_w<T, S, FX_PROD>(plan, a, s);
+    }
+    return fx_fail(FX_ERR_INVALID, "unknown reduce op %d", a.op);
+}
+
+}  // namespace
+
+bool fx_kernel_supported(int dtype, int wire, int op, bool broadcast) {
+    if (broadcast) return true;                       // bytes
+    if (dtype == FX_U8 || wire == FX_U8) return false;
+    if (dtype != wire && !(dtype == FX_F32 && wire == FX_BF16)) return false;
+    if (op == FX_AVG && (dtype == FX_I32 || dtype == FX_I64)) return false;
+    return op >= FX_SUM && op <= FX_PROD;
+}
+
+int fx_launch_allreduce(fx_plan* plan, const FxLaunch& a, cudaStream_t s) {
+    if (plan->dtype == FX_F32 && plan->wire == FX_BF16) return launch_allreduce_op<__nv_bfloat16, float>(plan, a, s);
+    switch (plan->wire) {
+        case FX_F32: return launch_allreduce_op<float, float>(plan, a, s);
+        case FX_BF16: return launch_allreduce_op<__nv_bfloat16, __nv_bfloat16>(plan, a, s);
+        case FX_F16: return launch_allreduce_op<__half, __half>(plan, a, s);
+        case FX_F64: return launch_allreduce_op<double, double>(plan, a, s);
+        case FX_I32: return launch_allreduce_op<int32_t, int32_t>(plan, a, s);
+        case FX_I64: return launch_allreduce_op<int64_t, int64_t>(plan, a, s);
+    }
+    return fx_fail(FX_ERR_INVALID, "all-reduce: unsupported dtype %d", plan->wire);
+}
+
+int fx_launch_broadcast(fx_plan* plan, const FxLaunch& a, cudaStream_t s) {
+    return launch(k_broadcast, plan, plan->grid_x, a, s);
+}
+
+int fx_launch_unpack(fx_plan* plan, const FxLaunch& a, cudaStream_t s) {
+    dim3 grid(plan->grid_x, a.n_local), block(FX_THREADS);
+    if (plan->dtype == FX_F32 && plan->wire == FX_BF16) k_unpack<__nv_bfloat16, float><<<grid, block, 0, s>>>(a);
+    else switch (plan->wire) {
+        case FX_F32: k_unpack<float, float><<<grid, block, 0, s>>>(a); break;
+        case FX_BF16: k_unpack<__nv_bfloat16, __nv_bfloat16><<<grid, block, 0, s>>>(a); break;
+        case FX_F16: k_unpack<__half, __half><<<grid, block, 0, s>>>(a); break;
+        case FX_F64: k_unpack<double, double><<<grid, block, 0, s>>>(a); break;
+        case FX_I32: k_unpack<int32_t, int32_t><<<grid, block, 0, s>>>(a); break;
+        case FX_I64: k_unpack<int64_t, int64_t><<<grid, block, 0, s>>>(a); break;
+        default: return fx_fail(FX_ERR_INVALID, "unpack: unsupported dtype %d", plan->wire);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fx_fail(FX_ERR_CUDA, "unpack launch failed: %s", cudaGetErrorString(e));
+    return FX_OK;
+}
+
+int fx_launch_barrier(fx_comm* comm, const FxLaunch& a, cudaStream_t s) {
+    (void)comm;
+    return launch(k_barrier, nullptr, 1, a, s);
+}
+
+int fx_max_coresident_blocks(int device, int n_local, int* sm_count) {
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return 0;
+    if (sm_count) *sm_count = sms;
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_two_shot<float, float, 8, FX_SUM>, FX_THREADS, 0) != cudaSuccess || occ < 1)
+        occ = 1;
+    occ = 1;                                           // every kernel is built for one CTA per SM
+    int blocks = sms * occ / (n_local > 0 ? n_local : 1);
+    if (blocks > FX_MAX_BLOCKS) blocks = FX_MAX_BLOCKS;
+    return blocks < 1 ? 1 : blocks;
+}
