@@ -1,0 +1,119 @@
+#!/usr/bin/env python
+"""BASELINE configs[4]: ``distrib.all_reduce`` bandwidth sweep 4 KiB - 1 GiB, and the
+``sync_model``-sized buckets of ResNet-18 / ResNet-50, next to the library path the reference
+calls (torch.distributed / NCCL: one flat all-reduce, and the reference's per-tensor loop).
+
+    torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 benchmarks/allreduce_sweep.py [--quick]
+
+Timing: CUDA events on the launching stream, >= 3 warm-ups, L2 flushed (256 MiB memset) before
+every timed iteration, mean over iterations, max over ranks.  busBW = 2 (W-1)/W * bytes / t.
+Writes one JSON object per line to stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+import torch                      # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--max-mb", type=int, default=1024)
+    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--no-nccl", action="store_true")
+    args = ap.parse_args()
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("cpu:gloo,cuda:nccl", init_method="env://")
+    from flashy_b200 import distrib
+    from flashy_b200 import context as fctx
+    from oracle.refdistrib import RefDistrib
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def timeit(fn, iters):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        total = 0.0
+        for _ in range(iters):
+            flush.zero_()
+            dist.barrier(device_ids=[local]) if False else None
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            total += e0.elapsed_time(e1)
+        t = torch.tensor([total / iters], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)          # gloo (CPU tensor)
+        return float(t[0])
+
+    def emit(**kw):
+        if rank == 0:
+            print(json.dumps(kw), flush=True)
+
+    bus = lambda nbytes, ms: 2 * (world - 1) / world * nbytes / (ms * 1e-3) / 1e9   # noqa: E731
+
+    # ------------------------------------------------------------------ flat all_reduce sweep
+    sizes = [4096 << k for k in range(0, 19)]
+    sizes = [s for s in sizes if s <= args.max_mb << 20]
+    if args.quick:
+        sizes = sizes[::3]
+    for dtype in (torch.float32, torch.bfloat16):
+        for nbytes in sizes:
+            n = nbytes // dtype.itemsize
+            x = torch.randn(n, device=dev, dtype=torch.float32).to(dtype)
+            iters = args.iters if nbytes <= (64 << 20) else max(5, args.iters // 4)
+            ours = timeit(lambda: distrib.all_reduce(x), iters)
+            row = dict(kind="all_reduce", dtype=str(dtype).split(".")[-1], bytes=nbytes, world=world,
+                       ours_ms=ours, ours_bus_gbs=bus(nbytes, ours))
+            if not args.no_nccl:
+                nccl = timeit(lambda: dist.all_reduce(x), iters)
+                row.update(nccl_ms=nccl, nccl_bus_gbs=bus(nbytes, nccl))
+            emit(**row)
+            del x
+
+    # ------------------------------------------------------------------ sync_model sized buckets
+    import torchvision
+    for name, ctor in (("resnet18", lambda: torchvision.models.resnet18(num_classes=10)),
+                       ("resnet50", torchvision.models.resnet50)):
+        for dtype in (torch.bfloat16, torch.float32):
+            torch.manual_seed(1234)
+            model = ctor().to(dev).to(dtype)
+            for p in model.parameters():
+                p.grad = torch.randn_like(p) * 1e-2
+            nbytes = sum(p.numel() for p in model.parameters()) * dtype.itemsize
+            ours = timeit(lambda: distrib.sync_model(model), args.iters)
+            grads_only = timeit(lambda: distrib.sync_gradients(model.parameters()), args.iters)
+            row = dict(kind="sync_model", model=name, dtype=str(dtype).split(".")[-1], grad_bytes=nbytes, world=world,
+                       ours_ms=ours, ours_grads_only_ms=grads_only, ours_bus_gbs=bus(nbytes, grads_only))
+            if not args.no_nccl:
+                ref = timeit(lambda: RefDistrib.sync_model(model), max(5, args.iters // 2))
+                flat = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
+                one = timeit(lambda: dist.all_reduce(flat), args.iters)
+                row.update(reference_path_nccl_ms=ref, nccl_flat_ms=one, nccl_flat_bus_gbs=bus(nbytes, one))
+            emit(**row)
+            del model
+    eng = fctx.current().engine
+    emit(kind="info", native_launches=eng.native_launches(), mem_kind=int(eng.info.mem_kind), world=world,
+         max_blocks=int(eng.info.max_blocks))
+    torch.cuda.synchronize()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
