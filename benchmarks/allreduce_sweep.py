@@ -109,7 +109,8 @@ def main():
             del model
     eng = fctx.current().engine
     emit(kind="info", native_launches=eng.native_launches(), mem_kind=int(eng.info.mem_kind), world=world,
-         max_blocks=int(eng.info.max_blocks))
+         max_blocks=int(eng.info.max_blocks), nvls=bool(eng.multicast), nvls_error=eng.multicast_error,
+         env={k: v for k, v in os.environ.items() if k.startswith("FLASHY_B200")})
     torch.cuda.synchronize()
     dist.barrier()
     dist.destroy_process_group()

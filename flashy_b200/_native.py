@@ -98,6 +98,7 @@ def _load() -> C.CDLL:
 
 
 lib = _load()
+C = C  # re-exported for the pointer-array fast path
 
 
 def check(rc: int) -> None:

@@ -505,10 +505,118 @@ extern "C" int fx_comm_connect(fx_comm* c, const void* blobs, size_t blob_len, i
     return FX_OK;
 }
 
+// Collective agreement over the host fabric: every rank reports `ok`; returns true iff all did.
+static bool all_agree(fx_comm* c, bool ok) {
+    int64_t sum = 0;
+    int eq = 0;
+    if (fx_host_exchange(c, 0, ok ? 1 : 0, 0x4d43u, &sum, &eq, 120.0) != FX_OK) return false;
+    return sum == c->world;
+}
+
 extern "C" int fx_comm_enable_multicast(fx_comm* c, const void* blobs, size_t blob_len, int n_procs) {
-    (void)blobs; (void)blob_len; (void)n_procs;
     if (!c) return fx_fail(FX_ERR_INVALID, "comm is NULL");
-    return fx_fail(FX_ERR_UNSUPPORTED, "NVLS multicast is not implemented in this build");
+    if (c->multicast) return FX_OK;
+    if (c->host_only || !c->connected) return fx_fail(FX_ERR_STATE, "multicast needs a connected device communicator");
+    if (c->n_local != 1 || c->world < 2)
+        return fx_fail(FX_ERR_UNSUPPORTED, "NVLS multicast needs one rank per process and at least two GPUs");
+    if (!blobs || blob_len != sizeof(FxBlob) || n_procs != c->world) return fx_fail(FX_ERR_INVALID, "multicast: need the export blobs of every process");
+    const FxBlob* all = static_cast<const FxBlob*>(blobs);
+    FxDriver& d = driver();
+    FxArena& mine = c->arena[c->rank0];
+    char why[256] = "";
+
+    // ---- step 0: can everybody do it at all?
+    bool ok = d.ok && d.MulticastCreate && d.MulticastAddDevice && d.MulticastBindMem && d.MulticastGetGranularity &&
+              c->mem_kind == FX_COMM_MEM_VMM && mine.vmm_handle != 0;
+    CUdevice dev = 0;
+    if (ok) {
+        int sup = 0;
+        ok = d.DeviceGet(&dev, c->device) == CUDA_SUCCESS &&
+             d.DeviceGetAttribute(&sup, CU_DEVICE_ATTRIBUTE_MULTICAST_SUPPORTED, dev) == CUDA_SUCCESS && sup == 1;
+        if (!ok) snprintf(why, sizeof(why), "device reports no multicast support");
+    } else {
+        snprintf(why, sizeof(why), "driver lacks cuMulticast* or arenas are not VMM allocations");
+    }
+    if (!all_agree(c, ok)) return fx_fail(FX_ERR_UNSUPPORTED, "multicast unavailable on at least one rank (%s)", why);
+
+    CUmulticastObjectProp prop = {};
+    prop.numDevices = (unsigned)c->world;
+    prop.handleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+    prop.flags = 0;
+    size_t gran = 0;
+    prop.size = mine.bytes;
+    ok = d.MulticastGetGranularity(&gran, &prop, CU_MULTICAST_GRANULARITY_MINIMUM) == CUDA_SUCCESS && gran > 0;
+    size_t mc_bytes = ok ? mine.bytes / gran * gran : 0;
+    ok = ok && mc_bytes >= (size_t)FX_PAD_BYTES + (1u << 20);
+    prop.size = mc_bytes;
+
+    // ---- step 1: rank 0 creates the object and exports it
+    CUmemGenericAllocationHandle mc = 0;
+    if (ok && c->rank0 == 0) {
+        CUresult r = d.MulticastCreate(&mc, &prop);
+        int fd = -1;
+        if (r == CUDA_SUCCESS) r = d.MemExportToShareableHandle(&fd, mc, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0);
+        ok = r == CUDA_SUCCESS;
+        if (ok) c->mc_fd = fd; else snprintf(why, sizeof(why), "cuMulticastCreate/export: %s", cu_err(r));
+    }
+    if (!all_agree(c, ok)) {
+        if (mc) d.MemRelease(mc);
+        return fx_fail(FX_ERR_UNSUPPORTED, "multicast object could not be created (%s)", why);
+    }
+    // ---- step 2: everyone else imports it; all add their device
+    if (c->rank0 != 0) {
+        int fd = fetch_fd(all[0].sock, 0, 1, 60.0);
+        ok = fd >= 0;
+        if (ok) {
+            CUresult r = d.MemImportFromShareableHandle(&mc, (void*)(uintptr_t)fd, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR);
+            close(fd);
+            ok = r == CUDA_SUCCESS;
+            if (!ok) snprintf(why, sizeof(why), "import of the multicast handle: %s", cu_err(r));
+        } else {
+            snprintf(why, sizeof(why), "could not fetch the multicast fd from rank 0");
+        }
+    }
+    if (ok) {
+        CUresult r = d.MulticastAddDevice(mc, dev);
+        ok = r == CUDA_SUCCESS;
+        if (!ok) snprintf(why, sizeof(why), "cuMulticastAddDevice: %s", cu_err(r));
+    }
+    if (!all_agree(c, ok)) {
+        if (mc) d.MemRelease(mc);
+        return fx_fail(FX_ERR_UNSUPPORTED, "multicast join failed (%s)", why);
+    }
+    // ---- step 3: bind this rank's arena at offset 0 (every device binds its own memory there)
+    {
+        CUresult r = d.MulticastBindMem(mc, 0, mine.vmm_handle, 0, mc_bytes, 0);
+        ok = r == CUDA_SUCCESS;
+        if (!ok) snprintf(why, sizeof(why), "cuMulticastBindMem: %s", cu_err(r));
+    }
+    if (!all_agree(c, ok)) {
+        d.MemRelease(mc);
+        return fx_fail(FX_ERR_UNSUPPORTED, "multicast bind failed (%s)", why);
+    }
+    // ---- step 4: map the multicast address range
+    CUdeviceptr va = 0;
+    {
+        CUresult r = d.MemAddressReserve(&va, mc_bytes, gran, 0, 0);
+        if (r == CUDA_SUCCESS) r = d.MemMap(va, mc_bytes, 0, mc, 0);
+        if (r == CUDA_SUCCESS) {
+            CUmemAccessDesc acc = {};
+            acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+            acc.location.id = c->device;
+            acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+            r = d.MemSetAccess(va, mc_bytes, &acc, 1);
+        }
+        ok = r == CUDA_SUCCESS;
+        if (!ok) snprintf(why, sizeof(why), "mapping the multicast range: %s", cu_err(r));
+    }
+    if (!all_agree(c, ok)) return fx_fail(FX_ERR_UNSUPPORTED, "multicast mapping failed (%s)", why);
+    std::lock_guard<std::mutex> lock(c->mu);
+    c->mc_handle = mc;
+    c->mc_base = reinterpret_cast<char*>(va);
+    c->mc_bytes = mc_bytes;
+    c->multicast = true;
+    return FX_OK;
 }
 
 extern "C" int fx_comm_get_info(fx_comm* c, fx_comm_info* info) {
@@ -646,7 +754,14 @@ extern "C" int fx_plan_create(fx_comm* c, int world, const int64_t* numels, int 
 
     const size_t data_bytes = (size_t)cur * wsize;
     const size_t one_shot_max = (size_t)env_ll("FLASHY_B200_ONE_SHOT_MAX", 256 << 10);
-    if (algo == FX_ALGO_AUTO) algo = (dtype != FX_U8 && data_bytes <= one_shot_max) ? FX_ALGO_ONE_SHOT : FX_ALGO_TWO_SHOT;
+    const size_t nvls_min = (size_t)env_ll("FLASHY_B200_NVLS_MIN", 512 << 10);
+    const bool nvls_ok = c && c->multicast && (wire_dtype == FX_F32 || wire_dtype == FX_BF16 || wire_dtype == FX_F16);
+    if (algo == FX_ALGO_NVLS && !nvls_ok) { delete p; return fx_fail(FX_ERR_UNSUPPORTED, "NVLS handles fp32 / bf16 / fp16 buckets only"); }
+    if (algo == FX_ALGO_AUTO) {
+        if (dtype != FX_U8 && data_bytes <= one_shot_max) algo = FX_ALGO_ONE_SHOT;
+        else if (nvls_ok && data_bytes >= nvls_min) algo = FX_ALGO_NVLS;
+        else algo = FX_ALGO_TWO_SHOT;
+    }
     if (dtype == FX_U8) algo = FX_ALGO_TWO_SHOT;            // broadcast uses the sharded layout
     p->algo = algo;
     const int shards = (algo == FX_ALGO_ONE_SHOT) ? 1 : world;
@@ -691,6 +806,7 @@ extern "C" int fx_plan_create(fx_comm* c, int world, const int64_t* numels, int 
         }
         p->region[0] += FX_PAD_BYTES;
         p->region[1] += FX_PAD_BYTES;
+        if (p->algo == FX_ALGO_NVLS && p->region[1] + need > c->mc_bytes) p->algo = FX_ALGO_TWO_SHOT;   // outside the multicast window
         cudaError_t e = cudaSetDevice(c->device);
         std::vector<long long> table(p->off);
         table.insert(table.end(), p->numel.begin(), p->numel.end());
@@ -848,7 +964,7 @@ extern "C" int fx_allreduce_begin(fx_plan* p, int op, const void* const* in_ptrs
     if (!p || !in_ptrs) return fx_fail(FX_ERR_INVALID, "NULL argument");
     fx_comm* c = p->comm;
     if (!c) return fx_fail(FX_ERR_STATE, "dry plan cannot be launched");
-    if (p->algo != FX_ALGO_TWO_SHOT) return fx_fail(FX_ERR_INVALID, "begin/finish needs a TWO_SHOT plan");
+    if (p->algo == FX_ALGO_ONE_SHOT) return fx_fail(FX_ERR_INVALID, "begin/finish needs a sharded (TWO_SHOT / NVLS) plan");
     if (!fx_kernel_supported(p->dtype, p->wire, op, false)) return fx_fail(FX_ERR_UNSUPPORTED, "all-reduce op %d on dtype %d is not supported", op, p->dtype);
     std::lock_guard<std::mutex> lock(c->mu);
     cudaStream_t s = static_cast<cudaStream_t>(stream);

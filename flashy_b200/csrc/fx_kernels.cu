@@ -432,6 +432,100 @@ __global__ void __launch_bounds__(FX_THREADS, 1) k_unpack(const FxLaunch a) {
     }
 }
 
+// ---------------------------------------------------------------------------- NVLS
+// multimem.ld_reduce: the NVSwitch reads the addressed 16 bytes from every GPU bound to the
+// multicast object, adds them (fp32 accumulation) and returns the sum; multimem.st writes the
+// 16 bytes into every GPU's copy.  Per GPU and direction this moves (1 + 1/W) N bytes instead
+// of the 2 (W-1)/W N of the peer-to-peer two-shot.
+template <typename T> struct Multimem;
+template <> struct Multimem<float> {
+    static __device__ __forceinline__ uint4 ld_reduce(const void* p) {
+        uint4 v;
+        asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+        return v;
+    }
+};
+template <> struct Multimem<__nv_bfloat16> {
+    static __device__ __forceinline__ uint4 ld_reduce(const void* p) {
+        uint4 v;
+        asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+        return v;
+    }
+};
+template <> struct Multimem<__half> {
+    static __device__ __forceinline__ uint4 ld_reduce(const void* p) {
+        uint4 v;
+        asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.f16x2 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+        return v;
+    }
+};
+__device__ __forceinline__ void multimem_st(void* p, const uint4& v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+template <typename T>
+__device__ __forceinline__ uint4 scale_vec(const uint4& raw, int world) {
+    using A = typename Acc<T>::type;
+    constexpr int VEC = FX_VEC_BYTES / sizeof(T);
+    Vec16<T> v;
+    v.u = raw;
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) v.e[e] = cvt<T, A>(cvt<A, T>(v.e[e]) / static_cast<A>(world));
+    return v.u;
+}
+
+template <typename T, typename S>
+__global__ void __launch_bounds__(FX_THREADS, 1) k_nvls(const FxLaunch a) {
+    const int l = blockIdx.y, b = blockIdx.x;
+    const int rank = a.rank0 + l;
+    const int world = a.world;
+    FxPlanState* st = a.state + l;
+    const uint32_t calls = ld_volatile_u32(&st->calls);
+    const unsigned long long region = a.region[calls & 1];
+    char* my = a.arena[rank];
+    T* stage = reinterpret_cast<T*>(my + region);
+    uint32_t epoch = pad_of(my)->block_epoch[b];
+    const long long slice = a.slice_elems, shard = a.shard_elems;
+    const bool avg = a.op == FX_AVG;
+
+    for (int s = 0; s < world; ++s) {
+        const long long lo = s * shard + b * slice;
+        pack_range<T, S>(a, l, stage, lo, lo + slice);
+    }
+    block_barrier(a, rank, world, b, ++epoch);
+    {
+        constexpr int U = 4;
+        const long long lo = rank * shard + b * slice;
+        char* mc = a.mc_arena + region + (unsigned long long)lo * sizeof(T);
+        const long long nvec = slice / (FX_VEC_BYTES / (long long)sizeof(T));
+        for (long long v0 = threadIdx.x; v0 < nvec; v0 += (long long)U * FX_THREADS) {
+            uint4 raw[U];
+#pragma unroll
+            for (int k = 0; k < U; ++k) {
+                const long long v = v0 + (long long)k * FX_THREADS;
+                if (v < nvec) raw[k] = Multimem<T>::ld_reduce(mc + v * FX_VEC_BYTES);
+            }
+#pragma unroll
+            for (int k = 0; k < U; ++k) {
+                const long long v = v0 + (long long)k * FX_THREADS;
+                if (v < nvec) multimem_st(mc + v * FX_VEC_BYTES, avg ? scale_vec<T>(raw[k], world) : raw[k]);
+            }
+        }
+    }
+    block_barrier(a, rank, world, b, ++epoch);
+    if (a.mode == FX_MODE_FUSED) {
+        for (int s = 0; s < world; ++s) {
+            const long long lo = s * shard + b * slice;
+            unpack_range<T, S>(a, l, stage, lo, lo + slice);
+        }
+    }
+    finish_launch(st, pad_of(my), b, epoch, calls);
+}
+
 __global__ void __launch_bounds__(FX_THREADS, 1) k_barrier(const FxLaunch a) {
     const int rank = a.rank0 + blockIdx.y;
     FxPad* pad = pad_of(a.arena[rank]);
@@ -462,6 +556,7 @@ int launch(K kernel, const fx_plan* plan, int grid_x, const FxLaunch& args, cuda
 template <typename T, typename S, int OP>
 int launch_allreduce_w(fx_plan* plan, const FxLaunch& a, cudaStream_t s) {
     if (plan->algo == FX_ALGO_ONE_SHOT) return launch(k_one_shot<T, S, OP>, plan, plan->grid_x, a, s);
+    // (an NVLS plan asked for MAX / MIN / PROD lands here: same sharded layout, peer-to-peer kernel)
     if (OP == FX_SUM) {
         switch (a.world) {
             case 2: return launch(k_two_shot<T, S, 2, OP>, plan, plan->grid_x, a, s);
@@ -495,6 +590,16 @@ bool fx_kernel_supported(int dtype, int wire, int op, bool broadcast) {
 }
 
 int fx_launch_allreduce(fx_plan* plan, const FxLaunch& a, cudaStream_t s) {
+    if (plan->algo == FX_ALGO_NVLS && (a.op == FX_SUM || a.op == FX_AVG)) {
+        if (!a.mc_arena) return fx_fail(FX_ERR_STATE, "NVLS plan without a multicast mapping");
+        if (plan->dtype == FX_F32 && plan->wire == FX_BF16) return launch(k_nvls<__nv_bfloat16, float>, plan, plan->grid_x, a, s);
+        switch (plan->wire) {
+            case FX_F32: return launch(k_nvls<float, float>, plan, plan->grid_x, a, s);
+            case FX_BF16: return launch(k_nvls<__nv_bfloat16, __nv_bfloat16>, plan, plan->grid_x, a, s);
+            case FX_F16: return launch(k_nvls<__half, __half>, plan, plan->grid_x, a, s);
+        }
+        return fx_fail(FX_ERR_UNSUPPORTED, "NVLS supports fp32 / bf16 / fp16 sums only");
+    }
     if (plan->dtype == FX_F32 && plan->wire == FX_BF16) return launch_allreduce_op<__nv_bfloat16, float>(plan, a, s);
     switch (plan->wire) {
         case FX_F32: return launch_allreduce_op<float, float>(plan, a, s);

@@ -22,6 +22,7 @@ import os
 import pickle
 import threading
 import typing as tp
+import weakref
 from contextlib import contextmanager
 from functools import wraps
 
@@ -127,20 +128,30 @@ def _flat(t: torch.Tensor, device: int) -> tp.Tuple[int, int, int]:
     return fx, t.data_ptr(), t.numel() * mult
 
 
-def _signature(tensors: tp.Sequence[torch.Tensor]) -> int:
-    # ints and bools only: their hashes do not depend on PYTHONHASHSEED, so every process agrees
-    return hash(tuple((t.element_size(), t.is_complex(), t.is_floating_point(), t.numel())
-                      for t in tensors)) & (2 ** 64 - 1)
+# A dtype code that is the same integer in every process (hash(torch.dtype) is not).
+_DT_CODE = {dt: i for i, dt in enumerate((
+    torch.float32, torch.bfloat16, torch.float16, torch.float64, torch.int32, torch.int64,
+    torch.complex64, torch.complex128, torch.uint8, torch.int8, torch.int16, torch.bool))}
 
 
-def _check_number_of_params(params: tp.Sequence[torch.Tensor]) -> None:
+def _list_key(tensors: tp.Sequence[torch.Tensor]) -> tp.Tuple[tp.Tuple[int, ...], tp.Tuple[int, ...]]:
+    """(dtype codes, numels): what ranks must agree on, and what a bucket layout depends on."""
+    return (tuple([_DT_CODE.get(t.dtype, -1) for t in tensors]), tuple([t.numel() for t in tensors]))
+
+
+def _key_signature(key) -> int:
+    return hash(key) & (2 ** 64 - 1)          # tuples of ints: independent of PYTHONHASHSEED
+
+
+def _check_number_of_params(params: tp.Sequence[torch.Tensor], key=None) -> None:
     """Reference flashy/distrib.py:78-89, without its device all-reduce and ``.item()`` sync:
     the counts meet in host shared memory.  Raises on EVERY rank if any rank differs."""
     ctx = _context.current()
     if ctx.world == 1 or not params:
         return
     engine = _engine(ctx, params)
-    total, same = engine.host_exchange(ctx.local, len(params), _sig_cached(params))
+    sig = _key_signature(key if key is not None else _list_key(params))
+    total, same = engine.host_exchange(ctx.local, len(params), sig)
     if total != len(params) * ctx.world:
         raise RuntimeError(f"Mismatch in number of params: ours is {len(params)}, "
                            "at least one worker has a different one.")
@@ -149,13 +160,9 @@ def _check_number_of_params(params: tp.Sequence[torch.Tensor]) -> None:
                            "at least one worker passed a different list.")
 
 
-def _sig_cached(params: tp.Sequence[torch.Tensor]) -> int:
-    return _signature(params)
-
-
-def _launch_streams(engine: Engine, payloads: tp.Sequence[tp.Any], launch: tp.Callable[[int], None]):
-    """Run ``launch(stream_handle)`` ordered after every hosted rank's current stream.  Returns
-    an event the ranks must wait on, or None when everything already sits on one stream."""
+def _launch_streams(engine: Engine, payloads: tp.Sequence[tp.Any], launch: tp.Callable[[tp.Any], None]):
+    """Run ``launch(stream)`` ordered after every hosted rank's current stream.  Returns an
+    event the ranks must wait on, or None when everything already sits on one stream."""
     streams = [p["stream"] for p in payloads]
     handles = {s.cuda_stream for s in streams}
     if len(handles) == 1:
@@ -176,73 +183,152 @@ def _launch_streams(engine: Engine, payloads: tp.Sequence[tp.Any], launch: tp.Ca
     return done
 
 
-def _collective(ctx, engine: Engine, kind: str, items: tp.Sequence[_Item], dtype: int, op: int = N.FX_AVG,
-                src: int = 0) -> None:
-    """One bucketed collective over ``items`` (all of fx dtype ``dtype``) for this rank."""
-    wire = N.FX_BF16 if (engine.wire_bf16 and dtype == N.FX_F32 and kind == "ar" and op in (N.FX_AVG, N.FX_SUM)) else dtype
-    esize = _ESIZE[dtype]
-    for bucket in _split(engine, items, _ESIZE[wire], esize):
-        numels = tuple(it.numel for it in bucket)
-        plan = engine.get_plan(kind, numels, dtype, wire)
-        payload = {"in": [it.src for it in bucket], "out": [it.dst for it in bucket],
+class _Bucket:
+    """One launch: which tensors (index into the list, byte offset for cut tensors) it covers."""
+    __slots__ = ("plan", "idx", "off", "plain", "in_arr", "out_arr")
+
+    def __init__(self, plan, idx, off):
+        self.plan, self.idx, self.off = plan, idx, off
+        self.plain = not any(off)
+        n = len(idx)
+        self.in_arr = (N.C.c_void_p * n)()
+        self.out_arr = (N.C.c_void_p * n)()
+
+
+class _Layout:
+    """Bucket plan of one ordered tensor list (cached by dtype/numel signature)."""
+    __slots__ = ("kind", "buckets", "used", "last_in", "last_out", "fresh")
+
+    def __init__(self, kind, buckets, used):
+        self.kind, self.buckets, self.used = kind, buckets, used
+        self.last_in = self.last_out = None
+        self.fresh = True
+
+
+def _build_layout(engine: Engine, kind: str, tensors: tp.Sequence[torch.Tensor], op: int) -> _Layout:
+    """Validate the tensors, group them by fx dtype in first-appearance order (identical on
+    every rank because the lists are), cut into buckets of at most ``bucket_cap`` wire bytes."""
+    groups: tp.Dict[int, tp.List[tp.Tuple[int, int]]] = {}
+    used = []
+    for i, t in enumerate(tensors):
+        fx, _, numel = _flat(t, engine.device)
+        if not numel:
+            continue
+        used.append(i)
+        if kind == "bc":
+            groups.setdefault(N.FX_U8, []).append((i, numel * _ESIZE[fx]))
+        else:
+            groups.setdefault(fx, []).append((i, numel))
+    buckets = []
+    for fx, items in groups.items():
+        wire = N.FX_BF16 if (engine.wire_bf16 and fx == N.FX_F32 and kind == "ar" and op in (N.FX_AVG, N.FX_SUM)) else fx
+        esize = _ESIZE[fx]
+        cap = max(engine.bucket_cap // _ESIZE[wire], 64)
+        cap -= cap % 64
+        cur_idx, cur_off, cur_n, fill = [], [], [], 0
+
+        def flush():
+            nonlocal cur_idx, cur_off, cur_n, fill
+            if cur_idx:
+                plan = engine.get_plan(kind, tuple(cur_n), fx, wire)
+                buckets.append(_Bucket(plan, cur_idx, cur_off))
+            cur_idx, cur_off, cur_n, fill = [], [], [], 0
+
+        for i, numel in items:
+            if numel > cap:                       # one tensor larger than a bucket: cut it
+                flush()
+                done = 0
+                while done < numel:
+                    n = min(cap, numel - done)
+                    cur_idx, cur_off, cur_n = [i], [done * esize], [n]
+                    flush()
+                    done += n
+                continue
+            if cur_idx and fill + numel > cap:
+                flush()
+            cur_idx.append(i)
+            cur_off.append(0)
+            cur_n.append(numel)
+            fill += numel
+        flush()
+    return _Layout(kind, buckets, used)
+
+
+def _dense_or_raise(tensors: tp.Sequence[torch.Tensor]) -> None:
+    for t in tensors:
+        if not t.is_contiguous() and not _dense(t):
+            raise ValueError("Tensors must be contiguous")
+
+
+def _run_layout(ctx, engine: Engine, layout: _Layout, ins: tp.Sequence[torch.Tensor],
+                outs: tp.Optional[tp.Sequence[torch.Tensor]], op: int, src: int = 0) -> None:
+    """Launch every bucket of ``layout`` on the tensors' current addresses."""
+    in_ptrs = [t.data_ptr() for t in ins]
+    out_ptrs = in_ptrs if outs is None else [t.data_ptr() for t in outs]
+    kind = layout.kind
+    if ctx.n_local == 1:
+        # production layout: straight into the C ABI on the current stream
+        stream = torch.cuda.current_stream()
+        refresh = in_ptrs != layout.last_in or out_ptrs != layout.last_out
+        for b in layout.buckets:
+            if refresh:
+                if b.plain:
+                    b.in_arr[:] = [in_ptrs[i] for i in b.idx]
+                    b.out_arr[:] = [out_ptrs[i] for i in b.idx]
+                else:
+                    b.in_arr[:] = [in_ptrs[i] + o for i, o in zip(b.idx, b.off)]
+                    b.out_arr[:] = [out_ptrs[i] + o for i, o in zip(b.idx, b.off)]
+            if kind == "ar":
+                engine.allreduce_raw(b.plan, op, b.in_arr, b.out_arr, stream)
+            else:
+                engine.broadcast_raw(b.plan, src, b.out_arr, stream)
+        layout.last_in, layout.last_out = in_ptrs, out_ptrs
+        return
+    for b in layout.buckets:                       # hosted (virtual) ranks meet, then ONE launch
+        payload = {"in": [in_ptrs[i] + o for i, o in zip(b.idx, b.off)],
+                   "out": [out_ptrs[i] + o for i, o in zip(b.idx, b.off)],
                    "stream": torch.cuda.current_stream()}
 
-        def lead(payloads, plan=plan):
-            ins = [p["in"] for p in payloads]
-            outs = [p["out"] for p in payloads]
+        def lead(payloads, plan=b.plan):
+            rows_in = [p["in"] for p in payloads]
+            rows_out = [p["out"] for p in payloads]
             if kind == "ar":
-                return _launch_streams(engine, payloads, lambda s: engine.allreduce(plan, op, ins, outs, s))
-            return _launch_streams(engine, payloads, lambda s: engine.broadcast(plan, src, outs, s))
+                return _launch_streams(engine, payloads, lambda s: engine.allreduce(plan, op, rows_in, rows_out, s))
+            return _launch_streams(engine, payloads, lambda s: engine.broadcast(plan, src, rows_out, s))
 
         done = ctx.rendezvous(payload, lead)
         if done is not None:
             torch.cuda.current_stream().wait_event(done)
 
 
-def _split(engine: Engine, items: tp.Sequence[_Item], wire_size: int, esize: int) -> tp.List[tp.List[_Item]]:
-    cap = max(engine.bucket_cap // wire_size, 64)
-    cap -= cap % 64
-    out: tp.List[tp.List[_Item]] = []
-    cur: tp.List[_Item] = []
-    used = 0
-    for it in items:
-        if it.numel > cap:                      # one tensor larger than a bucket: cut it
-            if cur:
-                out.append(cur)
-                cur, used = [], 0
-            done = 0
-            while done < it.numel:
-                n = min(cap, it.numel - done)
-                out.append([_Item(it.src + done * esize, it.dst + done * esize, n)])
-                done += n
-            continue
-        if cur and used + it.numel > cap:
-            out.append(cur)
-            cur, used = [], 0
-        cur.append(it)
-        used += it.numel
-    if cur:
-        out.append(cur)
-    return out
+def _layout_for(ctx, engine: Engine, kind: str, tensors: tp.Sequence[torch.Tensor], op: int, key) -> _Layout:
+    full = (kind, key, engine.wire_bf16 and op in (N.FX_AVG, N.FX_SUM))
+    layout = engine.layouts.get(full)
+    if layout is None or any(b.plan.handle is None for b in layout.buckets):
+        for _ in range(2):       # an arena eviction while building invalidates earlier buckets: redo once
+            layout = _build_layout(engine, kind, tensors, op)
+            if all(b.plan.handle is not None for b in layout.buckets):
+                break
+        engine.layouts[full] = layout
+    return layout
 
 
-def _reduce(ctx, ins: tp.Sequence[torch.Tensor], outs: tp.Sequence[torch.Tensor], op: int) -> None:
-    """Bucketed all-reduce of ``ins`` into ``outs`` (same objects for in-place), grouped by dtype
-    in first-appearance order (identical on every rank because the lists are)."""
+def _reduce(ctx, ins: tp.Sequence[torch.Tensor], outs: tp.Optional[tp.Sequence[torch.Tensor]], op: int,
+            key=None) -> None:
+    """Bucketed all-reduce of ``ins`` (into ``outs`` if given, else in place)."""
     engine = _engine(ctx, ins)
-    groups: tp.Dict[int, tp.List[_Item]] = {}
-    for tin, tout in zip(ins, outs):
-        fx, src, numel = _flat(tin, engine.device)
-        if tout is tin:
-            dst = src
-        else:
-            fx2, dst, numel2 = _flat(tout, engine.device)
-            if fx2 != fx or numel2 != numel:
-                raise RuntimeError("output tensor does not match the reduced tensor")
-        if numel:
-            groups.setdefault(fx, []).append(_Item(src, dst, numel))
-    for fx, items in groups.items():
-        _collective(ctx, engine, "ar", items, fx, op)
+    if engine.host_only:
+        _flat(ins[0], -1)                          # raises: no CPU fallback
+    key = key if key is not None else _list_key(ins)
+    layout = _layout_for(ctx, engine, "ar", ins, op, key)
+    _dense_or_raise(ins)
+    if outs is not None:
+        if _list_key(outs) != key:
+            raise RuntimeError("output tensors do not match the reduced tensors")
+        _dense_or_raise(outs)
+        for t in outs:
+            _flat(t, engine.device)
+    _run_layout(ctx, engine, layout, ins, outs, op)
 
 
 # ------------------------------------------------------------------------------------------
@@ -264,7 +350,7 @@ def all_reduce(tensor: torch.Tensor, op=distributed.ReduceOp.SUM):
     fx_op = _OPS.get(op)
     if fx_op is None:
         raise RuntimeError(f"reduce op {op} is not supported by flashy_b200")
-    _reduce(ctx, [tensor], [tensor], fx_op)
+    _reduce(ctx, [tensor], None, fx_op)
     return None
 
 
@@ -290,16 +376,27 @@ def wrap(model):
     return model
 
 
+def _average(ctx, todo: tp.List[torch.Tensor]) -> None:
+    """Count check + bucketed in-place mean of an already filtered list."""
+    key = _list_key(todo)
+    engine = _engine(ctx, todo)
+    full = ("ar", key, engine.wire_bf16)
+    known = full in engine.layouts
+    if not (known and engine.check_mode == "plan"):
+        _check_number_of_params(todo, key)
+    _reduce(ctx, todo, None, N.FX_AVG, key)
+
+
 def average_tensors(tensors: tp.Iterable[torch.Tensor]) -> None:
     """In-place mean over ranks of every float/complex tensor (flashy/distrib.py:96-111);
     other dtypes are ignored.  One bucketed kernel instead of a collective per tensor."""
     ctx = _context.current()
     if ctx.world == 1:
         return
-    todo = [t for t in tensors if _is_complex_or_float(t)]
-    _check_number_of_params(todo)
-    if todo:
-        _reduce(ctx, [t.data for t in todo], [t.data for t in todo], N.FX_AVG)
+    todo = [t for t in tensors if t.dtype.is_floating_point or t.dtype.is_complex]
+    if not todo:
+        return
+    _average(ctx, todo)
 
 
 def broadcast_tensors(tensors: tp.Iterable[torch.Tensor], src: int = 0) -> None:
@@ -307,18 +404,17 @@ def broadcast_tensors(tensors: tp.Iterable[torch.Tensor], src: int = 0) -> None:
     ctx = _context.current()
     if ctx.world == 1:
         return
-    todo = [t for t in tensors if _is_complex_or_float(t)]
-    _check_number_of_params(todo)
+    todo = [t for t in tensors if t.dtype.is_floating_point or t.dtype.is_complex]
     if not todo:
         return
+    key = _list_key(todo)
+    _check_number_of_params(todo, key)
     engine = _engine(ctx, todo)
-    items = []
-    for t in todo:
-        fx, ptr, numel = _flat(t.data, engine.device)
-        if numel:
-            items.append(_Item(ptr, ptr, numel * _ESIZE[fx]))     # bytes
-    if items:
-        _collective(ctx, engine, "bc", items, N.FX_U8, src=src)
+    if engine.host_only:
+        _flat(todo[0], -1)
+    layout = _layout_for(ctx, engine, "bc", todo, N.FX_SUM, key)
+    _dense_or_raise(todo)
+    _run_layout(ctx, engine, layout, todo, None, N.FX_SUM, src)
 
 
 def broadcast_model(model: torch.nn.Module, src: int = 0) -> None:
@@ -337,9 +433,9 @@ def _sync_buffers(model: torch.nn.Module, sync_buffers: bool, average_buffers: b
     if not sync_buffers:
         return
     if average_buffers:
-        average_tensors(model.buffers())
+        average_tensors(_model_lists(model)[1])
     else:
-        broadcast_tensors(model.buffers())
+        broadcast_tensors(_model_lists(model)[1])
 
 
 def sync_buffers(model: torch.nn.Module, average: bool = True) -> None:
@@ -348,10 +444,37 @@ def sync_buffers(model: torch.nn.Module, average: bool = True) -> None:
     _sync_buffers(model, True, average)
 
 
+class _ModelLists:
+    __slots__ = ("params", "buffers", "age")
+
+    def __init__(self, model):
+        self.params = list(model.parameters())
+        self.buffers = list(model.buffers())
+        self.age = 0
+
+
+_model_cache: "weakref.WeakKeyDictionary[torch.nn.Module, _ModelLists]" = weakref.WeakKeyDictionary()
+_MODEL_REVALIDATE = 64
+
+
+def _model_lists(model: torch.nn.Module) -> tp.Tuple[tp.List[torch.Tensor], tp.List[torch.Tensor]]:
+    """``list(model.parameters())`` / ``list(model.buffers())`` walk the whole module tree on
+    every call (~100 us for ResNet-18 -- more than the all-reduce itself takes on NVLink), so
+    the lists are cached per model and re-derived every 64 uses to pick up structural edits."""
+    entry = _model_cache.get(model)
+    if entry is None or entry.age >= _MODEL_REVALIDATE:
+        entry = _ModelLists(model)
+        _model_cache[model] = entry
+    entry.age += 1
+    return entry.params, entry.buffers
+
+
 def sync_model(model: torch.nn.Module, sync_buffers: bool = True, average_buffers: bool = True) -> None:
     """Call after ``backward()``: averages gradients and (by default) float buffers over ranks
     (flashy/distrib.py:193-210).  Returns once the work is enqueued on the current stream."""
-    sync_gradients(model.parameters())
+    if _context.current().world == 1:
+        return
+    sync_gradients(_model_lists(model)[0])
     _sync_buffers(model, sync_buffers, average_buffers)
 
 
@@ -452,7 +575,8 @@ def eager_sync_gradients(params: tp.Iterable[torch.Tensor]):
         for fx, idxs in layout:
             numels = tuple(params[i].numel() * _DTYPES[params[i].dtype][1] for i in idxs)
             wire = N.FX_BF16 if (engine.wire_bf16 and fx == N.FX_F32) else fx
-            specs.append((engine.get_plan("ar", numels, fx, wire, N.FX_ALGO_TWO_SHOT), len(idxs)))
+            algo = engine.sharded_algo(wire, sum(numels) * _ESIZE[wire])
+            specs.append((engine.get_plan("ar", numels, fx, wire, algo), len(idxs)))
         return _EagerSession(engine, ctx.n_local, specs)
 
     session: _EagerSession = ctx.rendezvous(None, make_session)

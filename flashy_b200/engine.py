@@ -80,6 +80,7 @@ class Engine:
             self.device = torch.cuda.current_device() if device is None else device
         arena = (arena_mb if arena_mb is not None else _env_int("FLASHY_B200_ARENA_MB", 512)) << 20
         self.comm = C.c_void_p()
+        self.multicast_error: tp.Optional[str] = None
         self._create(arena, N.FX_COMM_HOST_ONLY if self.host_only else N.FX_COMM_MEM_AUTO)
         if proc_world > 1:
             self._connect(arena)
@@ -91,6 +92,9 @@ class Engine:
         self.check_mode = os.environ.get("FLASHY_B200_CHECK", "always")
         self.wire_bf16 = os.environ.get("FLASHY_B200_WIRE", "") == "bf16"
         self.side_stream = None if self.host_only else torch.cuda.Stream(device=self.device)
+        self.layouts: tp.Dict[tp.Any, tp.Any] = {}       # bucket layouts of tensor lists (distrib.py)
+        self.multicast = bool(self.info.multicast)
+        self.nvls_min = _env_int("FLASHY_B200_NVLS_MIN", 512 << 10)
         self.profile = False
         self.timings: tp.List[tp.Tuple[tp.Any, tp.Any, tp.Any]] = []
 
@@ -119,6 +123,13 @@ class Engine:
         dist.all_gather_object(blobs, self._export())
         joined = b"".join(blobs)
         N.check(N.lib.fx_comm_connect(self.comm, joined, len(blobs[0]), self.proc_world))
+        dist.barrier()
+        # NVLS: bind every arena to one NVSwitch multicast object (collective; quietly stays on the
+        # peer-to-peer kernels where the system cannot do it).
+        if self.n_local == 1 and not self.host_only and os.environ.get("FLASHY_B200_NVLS", "1") != "0":
+            rc = N.lib.fx_comm_enable_multicast(self.comm, joined, len(blobs[0]), self.proc_world)
+            if rc != N.FX_OK:
+                self.multicast_error = N.lib.fx_last_error().decode(errors="replace")
         dist.barrier()
 
     def close(self) -> None:
@@ -160,6 +171,7 @@ class Engine:
                 for old in self.plans.values():
                     old.destroy()
                 self.plans.clear()
+                self.layouts.clear()
                 plan = Plan(self, key, numels, dtype, wire, algo)
             self.plans[key] = plan
             return plan
@@ -187,6 +199,20 @@ class Engine:
         ins, outs = self._rows(in_rows), self._rows(out_rows)
         self._timed(plan, stream, lambda: N.check(N.lib.fx_allreduce(plan.handle, op, ins, outs, stream.cuda_stream)))
 
+    def allreduce_raw(self, plan: Plan, op: int, in_arr, out_arr, stream) -> None:
+        """Fast path of the one-rank-per-process layout: prebuilt ctypes pointer arrays."""
+        if self.profile:
+            self._timed(plan, stream, lambda: N.check(N.lib.fx_allreduce(plan.handle, op, in_arr, out_arr, stream.cuda_stream)))
+            return
+        rc = N.lib.fx_allreduce(plan.handle, op, in_arr, out_arr, stream.cuda_stream)
+        if rc:
+            N.check(rc)
+
+    def broadcast_raw(self, plan: Plan, src: int, arr, stream) -> None:
+        rc = N.lib.fx_broadcast(plan.handle, src, arr, stream.cuda_stream)
+        if rc:
+            N.check(rc)
+
     def allreduce_begin(self, plan: Plan, op: int, in_rows, stream) -> None:
         ins = self._rows(in_rows)
         self._timed(plan, stream, lambda: N.check(N.lib.fx_allreduce_begin(plan.handle, op, ins, stream.cuda_stream)))
@@ -199,6 +225,12 @@ class Engine:
 
     def device_barrier(self, stream) -> None:
         N.check(N.lib.fx_barrier(self.comm, stream.cuda_stream))
+
+    def sharded_algo(self, dtype: int, wire_bytes: int) -> int:
+        """Algorithm for a begin/finish (eager) bucket: never one-shot."""
+        if self.multicast and dtype in (N.FX_F32, N.FX_BF16, N.FX_F16) and wire_bytes >= self.nvls_min:
+            return N.FX_ALGO_NVLS
+        return N.FX_ALGO_TWO_SHOT
 
     def poll(self) -> None:
         N.check(N.lib.fx_comm_poll(self.comm))
