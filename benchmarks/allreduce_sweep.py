@@ -61,6 +61,24 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)          # gloo (CPU tensor)
         return float(t[0])
 
+    def kernel_ms(fn, iters):
+        """Device time of our launches alone (CUDA events bracketing each launch on its stream),
+        summed per call: what the kernels cost once the host is not the bottleneck."""
+        eng = fctx.current().engine
+        fn()
+        torch.cuda.synchronize()
+        eng.profile, eng.timings = True, []
+        for _ in range(iters):
+            flush.zero_()
+            fn()
+        torch.cuda.synchronize()
+        eng.profile = False
+        total = sum(e0.elapsed_time(e1) for _, e0, e1 in eng.timings)
+        eng.timings = []
+        t = torch.tensor([total / iters], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
     def emit(**kw):
         if rank == 0:
             print(json.dumps(kw), flush=True)
@@ -78,8 +96,9 @@ def main():
             x = torch.randn(n, device=dev, dtype=torch.float32).to(dtype)
             iters = args.iters if nbytes <= (64 << 20) else max(5, args.iters // 4)
             ours = timeit(lambda: distrib.all_reduce(x), iters)
+            kern = kernel_ms(lambda: distrib.all_reduce(x), iters)
             row = dict(kind="all_reduce", dtype=str(dtype).split(".")[-1], bytes=nbytes, world=world,
-                       ours_ms=ours, ours_bus_gbs=bus(nbytes, ours))
+                       ours_ms=ours, ours_bus_gbs=bus(nbytes, ours), ours_kernel_ms=kern, ours_kernel_bus_gbs=bus(nbytes, kern))
             if not args.no_nccl:
                 nccl = timeit(lambda: dist.all_reduce(x), iters)
                 row.update(nccl_ms=nccl, nccl_bus_gbs=bus(nbytes, nccl))
@@ -98,8 +117,10 @@ def main():
             nbytes = sum(p.numel() for p in model.parameters()) * dtype.itemsize
             ours = timeit(lambda: distrib.sync_model(model), args.iters)
             grads_only = timeit(lambda: distrib.sync_gradients(model.parameters()), args.iters)
+            kern = kernel_ms(lambda: distrib.sync_model(model), args.iters)
             row = dict(kind="sync_model", model=name, dtype=str(dtype).split(".")[-1], grad_bytes=nbytes, world=world,
-                       ours_ms=ours, ours_grads_only_ms=grads_only, ours_bus_gbs=bus(nbytes, grads_only))
+                       ours_ms=ours, ours_grads_only_ms=grads_only, ours_bus_gbs=bus(nbytes, ours),
+                       ours_kernel_ms=kern, ours_kernel_bus_gbs=bus(nbytes, kern))
             if not args.no_nccl:
                 ref = timeit(lambda: RefDistrib.sync_model(model), max(5, args.iters // 2))
                 flat = torch.cat([p.grad.reshape(-1) for p in model.parameters()])

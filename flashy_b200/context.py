@@ -76,6 +76,9 @@ class ProcessContext(BaseContext):
     def engine(self) -> Engine:
         return self.engine_for(None)
 
+    def cached_engine(self) -> tp.Optional[Engine]:
+        return self._engine
+
     def rendezvous(self, payload, leader_fn):
         return leader_fn([payload])
 
@@ -97,6 +100,9 @@ class VirtualContext(BaseContext):
         return self.vworld.engine
 
     def engine_for(self, device, host_only: bool = False) -> Engine:
+        return self.vworld.engine
+
+    def cached_engine(self) -> tp.Optional[Engine]:
         return self.vworld.engine
 
     @property

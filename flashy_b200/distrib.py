@@ -106,9 +106,12 @@ def _is_complex_or_float(tensor: torch.Tensor) -> bool:
 
 def _engine(ctx, tensors: tp.Sequence[torch.Tensor]) -> Engine:
     """The communicator of the calling rank, created (collectively) on first use."""
-    cuda = [t for t in tensors if t.is_cuda]
+    eng = ctx.cached_engine()
+    if eng is not None:
+        return eng
     if not N.cuda_available():
         return ctx.engine_for(None, host_only=True)      # rendezvous fabric only; data calls will raise
+    cuda = [t for t in tensors if t.is_cuda]
     return ctx.engine_for(cuda[0].device.index if cuda else torch.cuda.current_device())
 
 
@@ -260,11 +263,9 @@ def _dense_or_raise(tensors: tp.Sequence[torch.Tensor]) -> None:
             raise ValueError("Tensors must be contiguous")
 
 
-def _run_layout(ctx, engine: Engine, layout: _Layout, ins: tp.Sequence[torch.Tensor],
-                outs: tp.Optional[tp.Sequence[torch.Tensor]], op: int, src: int = 0) -> None:
+def _run_layout(ctx, engine: Engine, layout: _Layout, in_ptrs: tp.List[int],
+                out_ptrs: tp.List[int], op: int, src: int = 0) -> None:
     """Launch every bucket of ``layout`` on the tensors' current addresses."""
-    in_ptrs = [t.data_ptr() for t in ins]
-    out_ptrs = in_ptrs if outs is None else [t.data_ptr() for t in outs]
     kind = layout.kind
     if ctx.n_local == 1:
         # production layout: straight into the C ABI on the current stream
@@ -328,7 +329,8 @@ def _reduce(ctx, ins: tp.Sequence[torch.Tensor], outs: tp.Optional[tp.Sequence[t
         _dense_or_raise(outs)
         for t in outs:
             _flat(t, engine.device)
-    _run_layout(ctx, engine, layout, ins, outs, op)
+    in_ptrs = [t.data_ptr() for t in ins]
+    _run_layout(ctx, engine, layout, in_ptrs, in_ptrs if outs is None else [t.data_ptr() for t in outs], op)
 
 
 # ------------------------------------------------------------------------------------------
@@ -414,7 +416,8 @@ def broadcast_tensors(tensors: tp.Iterable[torch.Tensor], src: int = 0) -> None:
         _flat(todo[0], -1)
     layout = _layout_for(ctx, engine, "bc", todo, N.FX_SUM, key)
     _dense_or_raise(todo)
-    _run_layout(ctx, engine, layout, todo, None, N.FX_SUM, src)
+    ptrs = [t.data_ptr() for t in todo]
+    _run_layout(ctx, engine, layout, ptrs, ptrs, N.FX_SUM, src)
 
 
 def broadcast_model(model: torch.nn.Module, src: int = 0) -> None:
@@ -433,9 +436,9 @@ def _sync_buffers(model: torch.nn.Module, sync_buffers: bool, average_buffers: b
     if not sync_buffers:
         return
     if average_buffers:
-        average_tensors(_model_lists(model)[1])
+        average_tensors(_model_entry(model).float_buffers)
     else:
-        broadcast_tensors(_model_lists(model)[1])
+        broadcast_tensors(_model_entry(model).float_buffers)
 
 
 def sync_buffers(model: torch.nn.Module, average: bool = True) -> None:
@@ -445,37 +448,87 @@ def sync_buffers(model: torch.nn.Module, average: bool = True) -> None:
 
 
 class _ModelLists:
-    __slots__ = ("params", "buffers", "age")
+    __slots__ = ("params", "buffers", "float_buffers", "age", "fast")
 
     def __init__(self, model):
         self.params = list(model.parameters())
         self.buffers = list(model.buffers())
+        self.float_buffers = [b for b in self.buffers if b.dtype.is_floating_point or b.dtype.is_complex]
         self.age = 0
+        self.fast: tp.Dict[tp.Any, tp.Any] = {}     # (tag, n) -> (key, layout) of a validated tensor list
 
 
 _model_cache: "weakref.WeakKeyDictionary[torch.nn.Module, _ModelLists]" = weakref.WeakKeyDictionary()
-_MODEL_REVALIDATE = 64
+_MODEL_REVALIDATE = 256
 
 
-def _model_lists(model: torch.nn.Module) -> tp.Tuple[tp.List[torch.Tensor], tp.List[torch.Tensor]]:
+def _model_entry(model: torch.nn.Module) -> _ModelLists:
     """``list(model.parameters())`` / ``list(model.buffers())`` walk the whole module tree on
     every call (~100 us for ResNet-18 -- more than the all-reduce itself takes on NVLink), so
-    the lists are cached per model and re-derived every 64 uses to pick up structural edits."""
+    the lists are cached per model and re-derived every 256 uses to pick up structural edits."""
     entry = _model_cache.get(model)
     if entry is None or entry.age >= _MODEL_REVALIDATE:
         entry = _ModelLists(model)
         _model_cache[model] = entry
     entry.age += 1
+    return entry
+
+
+def _model_lists(model: torch.nn.Module) -> tp.Tuple[tp.List[torch.Tensor], tp.List[torch.Tensor]]:
+    entry = _model_entry(model)
     return entry.params, entry.buffers
+
+
+def _average_cached(ctx, entry: _ModelLists, tag: str, todo: tp.List[torch.Tensor]) -> None:
+    """``average_tensors(todo)`` for a list derived from a cached model: the dtype/numel key and
+    the bucket layout are remembered per (tag, length) and re-validated whenever an address moves."""
+    if not todo:
+        return
+    engine = _engine(ctx, todo)
+    slot = (tag, len(todo), engine.wire_bf16)
+    cached = entry.fast.get(slot)
+    ptrs = [t.data_ptr() for t in todo]
+    if cached is not None and (ptrs == cached[1].last_in or _list_key(todo) == cached[0]) \
+            and all(b.plan.handle is not None for b in cached[1].buckets):
+        key, layout = cached
+        fresh = False
+    else:
+        key = _list_key(todo)
+        if engine.host_only:
+            _check_number_of_params(todo, key)
+            _flat(todo[0], -1)
+        layout = _layout_for(ctx, engine, "ar", todo, N.FX_AVG, key)
+        entry.fast[slot] = (key, layout)
+        fresh = True
+    if fresh or engine.check_mode != "plan":
+        _check_number_of_params(todo, key)
+    if ptrs != layout.last_in:
+        _dense_or_raise(todo)
+    _run_layout(ctx, engine, layout, ptrs, ptrs, N.FX_AVG)
 
 
 def sync_model(model: torch.nn.Module, sync_buffers: bool = True, average_buffers: bool = True) -> None:
     """Call after ``backward()``: averages gradients and (by default) float buffers over ranks
-    (flashy/distrib.py:193-210).  Returns once the work is enqueued on the current stream."""
-    if _context.current().world == 1:
+    (flashy/distrib.py:193-210).  Returns once the work is enqueued on the current stream.
+
+    With the default arguments the gradients and the float buffers of one dtype travel in ONE
+    bucket, i.e. one kernel launch for the whole model (the reference: one all-reduce and one
+    divide per tensor, in two passes)."""
+    ctx = _context.current()
+    if ctx.world == 1:
         return
-    sync_gradients(_model_lists(model)[0])
-    _sync_buffers(model, sync_buffers, average_buffers)
+    entry = _model_entry(model)
+    grads = [p.grad for p in entry.params]
+    for g in grads:
+        if g is None:
+            grads = [g for g in grads if g is not None]
+            break
+    if sync_buffers and average_buffers:
+        _average_cached(ctx, entry, "grads+buffers", grads + entry.float_buffers)
+    else:
+        _average_cached(ctx, entry, "grads", grads)
+        if sync_buffers:
+            broadcast_tensors(entry.float_buffers)
 
 
 # ------------------------------------------------------------------------------------------

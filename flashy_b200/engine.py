@@ -228,7 +228,8 @@ class Engine:
 
     def sharded_algo(self, dtype: int, wire_bytes: int) -> int:
         """Algorithm for a begin/finish (eager) bucket: never one-shot."""
-        if self.multicast and dtype in (N.FX_F32, N.FX_BF16, N.FX_F16) and wire_bytes >= self.nvls_min:
+        if (self.multicast and dtype in (N.FX_F32, N.FX_BF16, N.FX_F16) and wire_bytes >= self.nvls_min
+                and self.world >= _env_int("FLASHY_B200_NVLS_MIN_WORLD", 4)):
             return N.FX_ALGO_NVLS
         return N.FX_ALGO_TWO_SHOT
 

@@ -36,6 +36,7 @@ def _same(got, want, cols, nvls):
 def _worker(rank, world, nvls_env="1"):
     import os
     os.environ["FLASHY_B200_NVLS"] = nvls_env
+    os.environ["FLASHY_B200_NVLS_MIN_WORLD"] = "2"        # exercise the multimem kernel at every world size
     from oracle import numeric
     from flashy_b200 import distrib, context
     torch.cuda.set_device(rank % torch.cuda.device_count())
