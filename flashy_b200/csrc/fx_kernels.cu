@@ -164,23 +164,44 @@ __device__ __forceinline__ int find_tensor(const long long* off, int n, long lon
     return lo;
 }
 
-// Block-wide converting copy of `len` elements.  The vector path needs both ends 16-byte
+// Position of a thread inside the group of threads that works on one slice.
+struct Lane {
+    int tid, nth;
+};
+__device__ __forceinline__ Lane block_lane() { return Lane{(int)threadIdx.x, FX_THREADS}; }
+
+// The W slices a CTA packs / gathers per phase are independent: they are handed to disjoint
+// warp groups so that all W are in flight together (a serial loop over them pays W dependent
+// memory round trips, which dominates small buckets).  Slice index s is served by the warps
+// with warp % min(W, 16) == s; with W > 16 a group loops over s, s + 16, ...
+__device__ __forceinline__ Lane slice_lane(int world, int* first, int* step) {
+    constexpr int kWarps = FX_THREADS / 32;
+    const int groups = world < kWarps ? world : kWarps;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = warp % groups;
+    const int members = kWarps / groups + (g < kWarps % groups ? 1 : 0);
+    *first = g;
+    *step = groups;
+    return Lane{(warp / groups) * 32 + lane, members * 32};
+}
+
+// Group-wide converting copy of `len` elements.  The vector path needs both ends 16-byte
 // aligned (always true for the arena side; torch allocations make it true for the tensors in
 // practice); otherwise the whole range goes element by element.
 template <typename Src, typename Dst>
-__device__ __forceinline__ void copy_convert(const Src* __restrict__ src, Dst* __restrict__ dst, long long len) {
+__device__ __forceinline__ void copy_convert(const Src* __restrict__ src, Dst* __restrict__ dst, long long len, Lane ln) {
     constexpr int kMin = sizeof(Src) < sizeof(Dst) ? sizeof(Src) : sizeof(Dst);
     constexpr int UE = FX_VEC_BYTES / kMin;                    // elements per unit
     constexpr int NL = UE * sizeof(Src) / FX_VEC_BYTES;        // 16-byte loads per unit
     constexpr int NS = UE * sizeof(Dst) / FX_VEC_BYTES;        // 16-byte stores per unit
-    constexpr int U = NL >= 2 ? 2 : 4;                         // units in flight per thread
+    constexpr int U = NL >= 2 ? 4 : 8;                         // units in flight per thread
     const bool aligned = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0;
     const long long nunit = aligned ? len / UE : 0;
-    for (long long u0 = threadIdx.x; u0 < nunit; u0 += (long long)U * FX_THREADS) {
+    for (long long u0 = ln.tid; u0 < nunit; u0 += (long long)U * ln.nth) {
         Vec16<Src> in[U][NL];
 #pragma unroll
         for (int k = 0; k < U; ++k) {
-            const long long u = u0 + (long long)k * FX_THREADS;
+            const long long u = u0 + (long long)k * ln.nth;
             if (u < nunit) {
 #pragma unroll
                 for (int j = 0; j < NL; ++j)
@@ -189,7 +210,7 @@ __device__ __forceinline__ void copy_convert(const Src* __restrict__ src, Dst* _
         }
 #pragma unroll
         for (int k = 0; k < U; ++k) {
-            const long long u = u0 + (long long)k * FX_THREADS;
+            const long long u = u0 + (long long)k * ln.nth;
             if (u < nunit) {
                 Vec16<Dst> out[NS];
 #pragma unroll
@@ -203,41 +224,68 @@ __device__ __forceinline__ void copy_convert(const Src* __restrict__ src, Dst* _
             }
         }
     }
-    for (long long e = nunit * UE + threadIdx.x; e < len; e += FX_THREADS)
+    for (long long e = nunit * UE + ln.tid; e < len; e += ln.nth)
         dst[e] = cvt<Dst, Src>(src[e]);
 }
 
-// Calls f(i, s0, s1) for every tensor i overlapping bucket range [lo, hi): elements
-// [s0, s1) of the bucket belong to tensor i starting at tensor element s0 - off[i].
-template <typename F>
-__device__ __forceinline__ void for_each_segment(const Meta& a, long long lo, long long hi, F f) {
-    const long long* off = a.off;
-    const long long* numel = a.numel;
-    if (lo >= off[a.n]) return;                   // pure padding
-    for (int i = find_tensor(off, a.n, lo); i < a.n; ++i) {
-        const long long t0 = off[i];
-        if (t0 >= hi) break;
-        const long long s0 = lo > t0 ? lo : t0;
-        const long long t1 = t0 + numel[i];
-        const long long s1 = hi < t1 ? hi : t1;
-        if (s1 > s0) f(i, s0, s1);
+// Tensor index of bucket element e, walking forward from a known lower bound i.
+__device__ __forceinline__ int walk_tensor(const Meta& m, int i, long long e) {
+    while (i + 1 < m.n && m.off[i + 1] <= e) ++i;
+    return i;
+}
+
+// Move bucket range [lo, hi) between the tensors (type S) and the staging buffer (type T).
+// PACK: tensors -> stage, else stage -> tensors.  Ranges covered by one or two tensors use the
+// streaming copy per tensor; ranges crowded with small tensors (BatchNorm vectors, biases) are
+// walked unit by unit with a per-thread table lookup, so that their loads are all in flight
+// together instead of one short dependent copy per tensor.
+template <typename T, typename S, bool PACK>
+__device__ __forceinline__ void move_slice(const Meta& m, T* stage, long long lo, long long hi, Lane ln) {
+    if (lo >= m.off[m.n]) return;                              // pure padding
+    const int i0 = find_tensor(m.off, m.n, lo);
+    int nseg = 0;
+    for (int i = i0; i < m.n && m.off[i] < hi && nseg <= 2; ++i) nseg += (m.off[i] + m.numel[i] > lo);
+    if (nseg <= 2) {
+        for (int i = i0; i < m.n && m.off[i] < hi; ++i) {
+            const long long t0 = m.off[i], t1 = t0 + m.numel[i];
+            const long long s0 = lo > t0 ? lo : t0, s1 = hi < t1 ? hi : t1;
+            if (s1 <= s0) continue;
+            if (PACK) copy_convert<S, T>(static_cast<const S*>(m.in[i]) + (s0 - t0), stage + s0, s1 - s0, ln);
+            else copy_convert<T, S>(stage + s0, static_cast<S*>(m.out[i]) + (s0 - t0), s1 - s0, ln);
+        }
+        return;
+    }
+    constexpr int kMin = sizeof(S) < sizeof(T) ? sizeof(S) : sizeof(T);
+    constexpr int UE = FX_VEC_BYTES / kMin;
+    const long long nunit = (hi - lo) / UE;
+    for (long long u = ln.tid; u < nunit; u += ln.nth) {
+        const long long e = lo + u * UE;
+        const int i = walk_tensor(m, i0, e);
+        const long long t0 = m.off[i], t1 = t0 + m.numel[i];
+        if (e >= t1) continue;                                 // alignment padding between tensors
+        const int cnt = (t1 - e) < UE ? (int)(t1 - e) : UE;
+        T* st = stage + e;
+        if (PACK) {
+            const S* src = static_cast<const S*>(m.in[i]) + (e - t0);
+            if (cnt == UE && (reinterpret_cast<uintptr_t>(src) & 15) == 0) copy_convert<S, T>(src, st, UE, Lane{0, 1});
+            else for (int k = 0; k < cnt; ++k) st[k] = cvt<T, S>(src[k]);
+        } else {
+            S* dst = static_cast<S*>(m.out[i]) + (e - t0);
+            if (cnt == UE && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) copy_convert<T, S>(st, dst, UE, Lane{0, 1});
+            else for (int k = 0; k < cnt; ++k) dst[k] = cvt<S, T>(st[k]);
+        }
     }
 }
 
-template <typename T, typename S>
-__device__ __forceinline__ void pack_range(const Meta& m, T* stage, long long lo, long long hi) {
-    for_each_segment(m, lo, hi, [&](int i, long long s0, long long s1) {
-        const S* src = static_cast<const S*>(m.in[i]) + (s0 - m.off[i]);
-        copy_convert<S, T>(src, stage + s0, s1 - s0);
-    });
-}
-
-template <typename T, typename S>
-__device__ __forceinline__ void unpack_range(const Meta& m, const T* stage, long long lo, long long hi) {
-    for_each_segment(m, lo, hi, [&](int i, long long s0, long long s1) {
-        S* dst = static_cast<S*>(m.out[i]) + (s0 - m.off[i]);
-        copy_convert<T, S>(stage + s0, dst, s1 - s0);
-    });
+// All W slices `b` of a CTA (slice b of every shard), spread over the warp groups.
+template <typename T, typename S, bool PACK>
+__device__ __forceinline__ void move_all_slices(const Meta& m, T* stage, long long shard, long long slice, int b, int world) {
+    int first, step;
+    const Lane ln = slice_lane(world, &first, &step);
+    for (int s = first; s < world; s += step) {
+        const long long lo = s * shard + b * slice;
+        move_slice<T, S, PACK>(m, stage, lo, lo + slice, ln);
+    }
 }
 
 // ============================================================================ reductions
@@ -332,33 +380,45 @@ __device__ __forceinline__ void reduce_vectors(const FxLaunch& a, int world, uns
 }
 
 // One-shot tail: reduce bucket range [lo, hi) over all arenas and write the result straight
-// into the output tensors (no second staging pass, no second barrier).
+// into the output tensors (no second staging pass, no second barrier).  Unit by unit with a
+// per-thread table lookup; the W loads of a unit are issued together.
 template <typename T, typename S, int OP>
 __device__ __forceinline__ void reduce_unpack_range(const FxLaunch& a, const Meta& m, int world, unsigned long long region,
                                                     long long lo, long long hi, bool avg) {
     using A = typename Acc<T>::type;
     constexpr int VEC = FX_VEC_BYTES / sizeof(T);
-    for_each_segment(m, lo, hi, [&](int i, long long s0, long long s1) {
-        S* dst = static_cast<S*>(m.out[i]) + (s0 - m.off[i]);
-        const long long len = s1 - s0;
-        const long long nvec = (len + VEC - 1) / VEC;     // the last vector may run into padding
-        for (long long v = threadIdx.x; v < nvec; v += FX_THREADS) {
-            A acc[VEC];
-            for (int q = 0; q < world; ++q) {
-                const uint4* base = reinterpret_cast<const uint4*>(a.arena[q] + region) ;
-                accumulate<T, OP>(acc, ld16(reinterpret_cast<const char*>(base) + (s0 + v * VEC) * sizeof(T)), q == 0);
-            }
+    if (lo >= m.off[m.n]) return;
+    const int i0 = find_tensor(m.off, m.n, lo);
+    const long long nvec = (hi - lo) / VEC;
+    for (long long v = threadIdx.x; v < nvec; v += FX_THREADS) {
+        const long long e = lo + v * VEC;
+        const int i = walk_tensor(m, i0, e);
+        const long long t0 = m.off[i], t1 = t0 + m.numel[i];
+        if (e >= t1) continue;
+        const int cnt = (t1 - e) < VEC ? (int)(t1 - e) : VEC;
+        const unsigned long long byte_off = region + (unsigned long long)e * sizeof(T);
+        A acc[VEC];
+        if (world <= 8) {
+            uint4 raw[8];
 #pragma unroll
-            for (int e = 0; e < VEC; ++e) {
-                const long long idx = v * VEC + e;
-                if (idx < len) {
-                    A x = acc[e];
-                    if (avg) x = x / static_cast<A>(world);
-                    dst[idx] = cvt<S, T>(cvt<T, A>(x));      // round to the wire type first: same bits as two-shot
-                }
+            for (int q = 0; q < 8; ++q)
+                if (q < world) raw[q] = ld16(a.arena[q] + byte_off);
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if (q < world) accumulate<T, OP>(acc, raw[q], q == 0);
+        } else {
+            for (int q = 0; q < world; ++q) accumulate<T, OP>(acc, ld16(a.arena[q] + byte_off), q == 0);
+        }
+        S* dst = static_cast<S*>(m.out[i]) + (e - t0);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+            if (k < cnt) {
+                A x = acc[k];
+                if (avg) x = x / static_cast<A>(world);
+                dst[k] = cvt<S, T>(cvt<T, A>(x));              // round to the wire type first: same bits as two-shot
             }
         }
-    });
+    }
 }
 
 // ============================================================================ kernels
@@ -391,10 +451,7 @@ __global__ void __launch_bounds__(FX_THREADS, 1) k_two_shot(const FxLaunch a) {
     __shared__ MetaSmem meta_smem;
     const Meta m = load_meta(a, l, &meta_smem);
 
-    for (int s = 0; s < world; ++s) {
-        const long long lo = s * shard + b * slice;
-        pack_range<T, S>(m, stage, lo, lo + slice);
-    }
+    move_all_slices<T, S, true>(m, stage, shard, slice, b, world);
     block_barrier(a, rank, world, b, ++epoch);
 
     {
@@ -404,14 +461,18 @@ __global__ void __launch_bounds__(FX_THREADS, 1) k_two_shot(const FxLaunch a) {
     }
     block_barrier(a, rank, world, b, ++epoch);
 
-    for (int j = 0; j < world; ++j) {
-        const int s = (rank + j) % world;                     // stagger the peers
-        const long long lo = s * shard + b * slice;
-        const T* from = reinterpret_cast<const T*>(a.arena[s] + region);
-        if (a.mode == FX_MODE_FUSED) {
-            unpack_range<T, S>(m, from, lo, lo + slice);
-        } else if (s != rank) {
-            copy_convert<T, T>(from + lo, stage + lo, slice);
+    {
+        int first, step;
+        const Lane ln = slice_lane(world, &first, &step);
+        for (int j = first; j < world; j += step) {
+            const int s = (rank + j) % world;                 // every group pulls from a different peer
+            const long long lo = s * shard + b * slice;
+            T* from = reinterpret_cast<T*>(a.arena[s] + region);
+            if (a.mode == FX_MODE_FUSED) {
+                move_slice<T, S, false>(m, from, lo, lo + slice, ln);
+            } else if (s != rank) {
+                copy_convert<T, T>(from + lo, stage + lo, slice, ln);
+            }
         }
     }
     finish_launch(st, pad_of(my), b, epoch, calls);
@@ -430,7 +491,7 @@ __global__ void __launch_bounds__(FX_THREADS, 1) k_one_shot(const FxLaunch a) {
     const long long lo = b * a.slice_elems, hi = lo + a.slice_elems;
     __shared__ MetaSmem meta_smem;
     const Meta m = load_meta(a, l, &meta_smem);
-    pack_range<T, S>(m, reinterpret_cast<T*>(my + region), lo, hi);
+    move_slice<T, S, true>(m, reinterpret_cast<T*>(my + region), lo, hi, block_lane());
     block_barrier(a, rank, world, b, ++epoch);
     reduce_unpack_range<T, S, OP>(a, m, world, region, lo, hi, a.op == FX_AVG);
     finish_launch(st, pad_of(my), b, epoch, calls);
@@ -449,19 +510,16 @@ __global__ void __launch_bounds__(FX_THREADS, 1) k_broadcast(const FxLaunch a) {
     const long long slice = a.slice_elems, shard = a.shard_elems;
     __shared__ MetaSmem meta_smem;
     const Meta m = load_meta(a, l, &meta_smem);
-    if (rank == a.src) {
-        for (int s = 0; s < world; ++s) {
-            const long long lo = s * shard + b * slice;
-            pack_range<uint8_t, uint8_t>(m, reinterpret_cast<uint8_t*>(my + region), lo, lo + slice);
-        }
-    }
+    if (rank == a.src) move_all_slices<uint8_t, uint8_t, true>(m, reinterpret_cast<uint8_t*>(my + region), shard, slice, b, world);
     block_barrier(a, rank, world, b, ++epoch);
     if (rank != a.src) {
-        const uint8_t* from = reinterpret_cast<const uint8_t*>(a.arena[a.src] + region);
-        for (int j = 0; j < world; ++j) {
+        uint8_t* from = reinterpret_cast<uint8_t*>(a.arena[a.src] + region);
+        int first, step;
+        const Lane ln = slice_lane(world, &first, &step);
+        for (int j = first; j < world; j += step) {
             const int s = (rank + j) % world;                 // spread the readers over the source's memory
             const long long lo = s * shard + b * slice;
-            unpack_range<uint8_t, uint8_t>(m, from, lo, lo + slice);
+            move_slice<uint8_t, uint8_t, false>(m, from, lo, lo + slice, ln);
         }
     }
     finish_launch(st, pad_of(my), b, epoch, calls);
@@ -474,13 +532,10 @@ __global__ void __launch_bounds__(FX_THREADS, 1) k_unpack(const FxLaunch a) {
     const int rank = a.rank0 + l;
     const uint32_t calls = ld_volatile_u32(&a.state[l].calls);
     const unsigned long long region = a.region[(calls - 1) & 1];     // the region the matching BEGIN used
-    const T* stage = reinterpret_cast<const T*>(a.arena[rank] + region);
+    T* stage = reinterpret_cast<T*>(a.arena[rank] + region);
     __shared__ MetaSmem meta_smem;
     const Meta m = load_meta(a, l, &meta_smem);
-    for (int s = 0; s < a.world; ++s) {
-        const long long lo = s * a.shard_elems + b * a.slice_elems;
-        unpack_range<T, S>(m, stage, lo, lo + a.slice_elems);
-    }
+    move_all_slices<T, S, false>(m, stage, a.shard_elems, a.slice_elems, b, a.world);
 }
 
 // ---------------------------------------------------------------------------- NVLS
@@ -545,10 +600,7 @@ __global__ void __launch_bounds__(FX_THREADS, 1) k_nvls(const FxLaunch a) {
     __shared__ MetaSmem meta_smem;
     const Meta m = load_meta(a, l, &meta_smem);
 
-    for (int s = 0; s < world; ++s) {
-        const long long lo = s * shard + b * slice;
-        pack_range<T, S>(m, stage, lo, lo + slice);
-    }
+    move_all_slices<T, S, true>(m, stage, shard, slice, b, world);
     block_barrier(a, rank, world, b, ++epoch);
     {
         constexpr int U = 4;
@@ -570,12 +622,7 @@ __global__ void __launch_bounds__(FX_THREADS, 1) k_nvls(const FxLaunch a) {
         }
     }
     block_barrier(a, rank, world, b, ++epoch);
-    if (a.mode == FX_MODE_FUSED) {
-        for (int s = 0; s < world; ++s) {
-            const long long lo = s * shard + b * slice;
-            unpack_range<T, S>(m, stage, lo, lo + slice);
-        }
-    }
+    if (a.mode == FX_MODE_FUSED) move_all_slices<T, S, false>(m, stage, shard, slice, b, world);
     finish_launch(st, pad_of(my), b, epoch, calls);
 }
 
