@@ -234,30 +234,14 @@ __device__ __forceinline__ int walk_tensor(const Meta& m, int i, long long e) {
     return i;
 }
 
-// Move bucket range [lo, hi) between the tensors (type S) and the staging buffer (type T).
-// PACK: tensors -> stage, else stage -> tensors.  Ranges covered by one or two tensors use the
-// streaming copy per tensor; ranges crowded with small tensors (BatchNorm vectors, biases) are
-// walked unit by unit with a per-thread table lookup, so that their loads are all in flight
-// together instead of one short dependent copy per tensor.
+// Unit-by-unit move of bucket range [lo, hi) (a run of small tensors): every thread looks its
+// unit's tensor up in the shared-memory table, so all loads of the run are in flight together
+// instead of one short dependent copy per tensor.
 template <typename T, typename S, bool PACK>
-__device__ __forceinline__ void move_slice(const Meta& m, T* stage, long long lo, long long hi, Lane ln) {
-    if (lo >= m.off[m.n]) return;                              // pure padding
-    const int i0 = find_tensor(m.off, m.n, lo);
-    int nseg = 0;
-    for (int i = i0; i < m.n && m.off[i] < hi && nseg <= 2; ++i) nseg += (m.off[i] + m.numel[i] > lo);
-    if (nseg <= 2) {
-        for (int i = i0; i < m.n && m.off[i] < hi; ++i) {
-            const long long t0 = m.off[i], t1 = t0 + m.numel[i];
-            const long long s0 = lo > t0 ? lo : t0, s1 = hi < t1 ? hi : t1;
-            if (s1 <= s0) continue;
-            if (PACK) copy_convert<S, T>(static_cast<const S*>(m.in[i]) + (s0 - t0), stage + s0, s1 - s0, ln);
-            else copy_convert<T, S>(stage + s0, static_cast<S*>(m.out[i]) + (s0 - t0), s1 - s0, ln);
-        }
-        return;
-    }
+__device__ __forceinline__ void move_run(const Meta& m, T* stage, int i0, long long lo, long long hi, Lane ln) {
     constexpr int kMin = sizeof(S) < sizeof(T) ? sizeof(S) : sizeof(T);
     constexpr int UE = FX_VEC_BYTES / kMin;
-    const long long nunit = (hi - lo) / UE;
+    const long long nunit = (hi - lo + UE - 1) / UE;
     for (long long u = ln.tid; u < nunit; u += ln.nth) {
         const long long e = lo + u * UE;
         const int i = walk_tensor(m, i0, e);
@@ -275,6 +259,35 @@ __device__ __forceinline__ void move_slice(const Meta& m, T* stage, long long lo
             else for (int k = 0; k < cnt; ++k) dst[k] = cvt<S, T>(st[k]);
         }
     }
+}
+
+// Move bucket range [lo, hi) between the tensors (type S) and the staging buffer (type T).
+// PACK: tensors -> stage, else stage -> tensors.  Pieces of at least one unit per thread are
+// streamed with the unrolled group-wide copy; runs of smaller pieces (BatchNorm vectors,
+// biases) go through move_run.
+template <typename T, typename S, bool PACK>
+__device__ __forceinline__ void move_slice(const Meta& m, T* stage, long long lo, long long hi, Lane ln) {
+    if (lo >= m.off[m.n]) return;                              // pure padding
+    constexpr int kMin = sizeof(S) < sizeof(T) ? sizeof(S) : sizeof(T);
+    constexpr int UE = FX_VEC_BYTES / kMin;
+    const long long big = (long long)ln.nth * UE;
+    const int i0 = find_tensor(m.off, m.n, lo);
+    long long run_lo = -1, run_hi = 0;
+    int run_i0 = 0;
+    for (int i = i0; i < m.n && m.off[i] < hi; ++i) {
+        const long long t0 = m.off[i], t1 = t0 + m.numel[i];
+        const long long s0 = lo > t0 ? lo : t0, s1 = hi < t1 ? hi : t1;
+        if (s1 <= s0) continue;
+        if (s1 - s0 >= big) {
+            if (run_lo >= 0) { move_run<T, S, PACK>(m, stage, run_i0, run_lo, run_hi, ln); run_lo = -1; }
+            if (PACK) copy_convert<S, T>(static_cast<const S*>(m.in[i]) + (s0 - t0), stage + s0, s1 - s0, ln);
+            else copy_convert<T, S>(stage + s0, static_cast<S*>(m.out[i]) + (s0 - t0), s1 - s0, ln);
+        } else {
+            if (run_lo < 0) { run_lo = s0; run_i0 = i; }
+            run_hi = s1;
+        }
+    }
+    if (run_lo >= 0) move_run<T, S, PACK>(m, stage, run_i0, run_lo, run_hi, ln);
 }
 
 // All W slices `b` of a CTA (slice b of every shard), spread over the warp groups.
