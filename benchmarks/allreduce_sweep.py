@@ -30,6 +30,8 @@ def main():
     ap.add_argument("--max-mb", type=int, default=1024)
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--no-nccl", action="store_true")
+    ap.add_argument("--only-sync", action="store_true", help="skip the flat all_reduce sweep")
+    ap.add_argument("--tag", default="")
     args = ap.parse_args()
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
@@ -90,6 +92,8 @@ def main():
     sizes = [s for s in sizes if s <= args.max_mb << 20]
     if args.quick:
         sizes = sizes[::3]
+    if args.only_sync:
+        sizes = []
     for dtype in (torch.float32, torch.bfloat16):
         for nbytes in sizes:
             n = nbytes // dtype.itemsize
@@ -131,7 +135,7 @@ def main():
     eng = fctx.current().engine
     emit(kind="info", native_launches=eng.native_launches(), mem_kind=int(eng.info.mem_kind), world=world,
          max_blocks=int(eng.info.max_blocks), nvls=bool(eng.multicast), nvls_error=eng.multicast_error,
-         env={k: v for k, v in os.environ.items() if k.startswith("FLASHY_B200")})
+         tag=args.tag, env={k: v for k, v in os.environ.items() if k.startswith("FLASHY_B200")})
     torch.cuda.synchronize()
     dist.barrier()
     dist.destroy_process_group()

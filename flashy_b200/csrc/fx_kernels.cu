@@ -62,7 +62,8 @@ __device__ __forceinline__ void block_barrier(const FxLaunch& a, int rank, int w
     __syncthreads();
     if (threadIdx.x < world) {
         const int q = threadIdx.x;
-        __threadfence_system();
+        // release at system scope: the CTA's earlier writes (ordered before this thread by the
+        // bar.sync above) are visible to whoever acquires the flag
         st_release_sys(&pad_of(a.arena[q])->flags[b][rank], target);
         const uint32_t* mine = &pad_of(a.arena[rank])->flags[b][q];
         unsigned long long t0 = 0;
@@ -438,11 +439,9 @@ __device__ __forceinline__ void reduce_unpack_range(const FxLaunch& a, const Met
 __device__ __forceinline__ void finish_launch(FxPlanState* st, FxPad* pad, int b, uint32_t epoch, uint32_t calls) {
     __syncthreads();
     if (threadIdx.x == 0) {
-        pad->block_epoch[b] = epoch;
-        __threadfence();
+        pad->block_epoch[b] = epoch;                            // (visible to the next launch: kernel boundary)
         if (atomicAdd(&st->finished, 1u) == gridDim.x - 1) {    // last CTA of this hosted rank
             st->finished = 0;
-            __threadfence();
             *reinterpret_cast<volatile uint32_t*>(&st->calls) = calls + 1;
         }
     }
