@@ -779,6 +779,14 @@ extern "C" int fx_plan_create(fx_comm* c, int world, const int64_t* numels, int 
     p->shard = p->slice * grid;
     p->padded = p->shard * shards;
     p->wire_bytes = (size_t)p->padded * wsize;
+    // Pipelined kernel (pack / reduce / gather as concurrent warp roles): chunks of >= 2 KiB.
+    if (algo != FX_ALGO_ONE_SHOT && dtype != FX_U8 && env_ll("FLASHY_B200_PIPE", 1) != 0 &&
+        (wire_dtype == FX_F32 || wire_dtype == FX_BF16 || wire_dtype == FX_F16)) {
+        const long long chunk_target = env_ll("FLASHY_B200_CHUNK_BYTES", 4096) / (long long)wsize;
+        long long chunks = std::max<long long>(1, std::min<long long>(env_ll("FLASHY_B200_MAX_CHUNKS", 8), p->slice / std::max<long long>(chunk_target, slice_align)));
+        p->chunk = ((p->slice + chunks - 1) / chunks + slice_align - 1) / slice_align * slice_align;
+        p->chunks = (int)((p->slice + p->chunk - 1) / p->chunk);
+    }
 
     if (c && !c->host_only) {
         std::lock_guard<std::mutex> lock(c->mu);
@@ -885,6 +893,7 @@ static void fill_launch(fx_comm* c, fx_plan* p, FxLaunch& a) {
         a.state = p->d_state;
         a.region[0] = p->region[0]; a.region[1] = p->region[1];
         a.slice_elems = p->slice; a.shard_elems = p->shard;
+        a.chunks = p->chunks; a.chunk_elems = p->chunk;
     }
 }
 

@@ -11,7 +11,7 @@
 #include "../../include/flashy_b200.h"
 
 #define FX_THREADS 512                 // threads per CTA of every collective kernel
-#define FX_PAD_BYTES (64u << 10)       // signal pad at the head of each arena
+#define FX_PAD_BYTES (128u << 10)      // signal pad at the head of each arena
 #define FX_VEC_BYTES 16                // one 128-bit access
 #define FX_SLICE_ALIGN 128             // slices start on 128-byte lines (no line shared by two CTAs)
 
@@ -19,8 +19,11 @@
 // flags[b][q]  : written by rank q's CTA b (over NVLink or locally), polled by the owner's CTA b.
 // block_epoch  : owner-private; last barrier value CTA b used (monotonic, wraps mod 2^32).
 struct FxPad {
-    uint32_t flags[FX_MAX_BLOCKS][FX_MAX_WORLD];
+    uint32_t flags[FX_MAX_BLOCKS][FX_MAX_WORLD];        // CTA-wide barriers of the classic kernels
+    uint32_t flags_pack[FX_MAX_BLOCKS][FX_MAX_WORLD];   // pipelined kernel: "chunk c is packed on rank q"
+    uint32_t flags_red[FX_MAX_BLOCKS][FX_MAX_WORLD];    // pipelined kernel: "chunk c of shard q is reduced"
     uint32_t block_epoch[FX_MAX_BLOCKS];
+    uint32_t pipe_epoch[FX_MAX_BLOCKS];                 // owner-private base value of the two arrays above
 };
 static_assert(sizeof(FxPad) <= FX_PAD_BYTES, "signal pad too small");
 
@@ -54,6 +57,8 @@ struct FxLaunch {
     int op;                           // fx_op
     int src;                          // broadcast source rank
     int mode;                         // FxMode
+    int chunks;                       // > 0: pipelined kernel, chunks per slice
+    long long chunk_elems;            // elements per chunk (multiple of 128 bytes)
 };
 
 // ---------------------------------------------------------------- host objects
@@ -120,6 +125,8 @@ struct fx_plan {
     int grid_x = 1;
     std::vector<long long> numel, off;          // off has n+1 entries
     long long total = 0, padded = 0, shard = 0, slice = 0;
+    int chunks = 0;                             // pipelined kernel: chunks per slice (0 = classic kernels)
+    long long chunk = 0;
     size_t esize = 0, wsize = 0, wire_bytes = 0;
     size_t region[2] = {0, 0};
     bool recycled = false;                      // region memory was used by an earlier plan

@@ -335,7 +335,7 @@ __device__ __forceinline__ uint4 finalize(typename Acc<T>::type* acc, bool avg, 
 // world (all W loads of a vector in flight at once); W == 0: runtime world.
 template <typename T, int W, int OP>
 __device__ __forceinline__ void reduce_vectors(const FxLaunch& a, int world, unsigned long long byte_off,
-                                               long long nvec, bool avg, char* dst_arena) {
+                                               long long nvec, bool avg, char* dst_arena, Lane ln) {
     using A = typename Acc<T>::type;
     constexpr int VEC = FX_VEC_BYTES / sizeof(T);
     uint4* dst = reinterpret_cast<uint4*>(dst_arena + byte_off);
@@ -345,11 +345,11 @@ __device__ __forceinline__ void reduce_vectors(const FxLaunch& a, int world, uns
         const uint4* base[WW];
 #pragma unroll
         for (int q = 0; q < WW; ++q) base[q] = reinterpret_cast<const uint4*>(a.arena[q] + byte_off);
-        for (long long v0 = threadIdx.x; v0 < nvec; v0 += (long long)U * FX_THREADS) {
+        for (long long v0 = ln.tid; v0 < nvec; v0 += (long long)U * ln.nth) {
             uint4 raw[U][WW];
 #pragma unroll
             for (int k = 0; k < U; ++k) {
-                const long long v = v0 + (long long)k * FX_THREADS;
+                const long long v = v0 + (long long)k * ln.nth;
                 if (v < nvec) {
 #pragma unroll
                     for (int q = 0; q < WW; ++q) raw[k][q] = ld16(base[q] + v);
@@ -357,7 +357,7 @@ __device__ __forceinline__ void reduce_vectors(const FxLaunch& a, int world, uns
             }
 #pragma unroll
             for (int k = 0; k < U; ++k) {
-                const long long v = v0 + (long long)k * FX_THREADS;
+                const long long v = v0 + (long long)k * ln.nth;
                 if (v < nvec) {
                     A acc[VEC];
 #pragma unroll
@@ -368,25 +368,25 @@ __device__ __forceinline__ void reduce_vectors(const FxLaunch& a, int world, uns
         }
     } else {
         constexpr int U = 4;
-        for (long long v0 = threadIdx.x; v0 < nvec; v0 += (long long)U * FX_THREADS) {
+        for (long long v0 = ln.tid; v0 < nvec; v0 += (long long)U * ln.nth) {
             A acc[U][VEC];
             for (int q = 0; q < world; ++q) {
                 const uint4* base = reinterpret_cast<const uint4*>(a.arena[q] + byte_off);
                 uint4 raw[U];
 #pragma unroll
                 for (int k = 0; k < U; ++k) {
-                    const long long v = v0 + (long long)k * FX_THREADS;
+                    const long long v = v0 + (long long)k * ln.nth;
                     if (v < nvec) raw[k] = ld16(base + v);
                 }
 #pragma unroll
                 for (int k = 0; k < U; ++k) {
-                    const long long v = v0 + (long long)k * FX_THREADS;
+                    const long long v = v0 + (long long)k * ln.nth;
                     if (v < nvec) accumulate<T, OP>(acc[k], raw[k], q == 0);
                 }
             }
 #pragma unroll
             for (int k = 0; k < U; ++k) {
-                const long long v = v0 + (long long)k * FX_THREADS;
+                const long long v = v0 + (long long)k * ln.nth;
                 if (v < nvec) st16(dst + v, finalize<T>(acc[k], avg, world));
             }
         }
@@ -469,7 +469,7 @@ __global__ void __launch_bounds__(FX_THREADS, 1) k_two_shot(const FxLaunch a) {
     {
         const long long lo = rank * shard + b * slice;
         reduce_vectors<T, W, OP>(a, world, region + (unsigned long long)lo * sizeof(T),
-                                 slice / (FX_VEC_BYTES / (long long)sizeof(T)), avg, my);
+                                 slice / (FX_VEC_BYTES / (long long)sizeof(T)), avg, my, block_lane());
     }
     block_barrier(a, rank, world, b, ++epoch);
 
@@ -596,6 +596,25 @@ __device__ __forceinline__ uint4 scale_vec(const uint4& raw, int world) {
     return v.u;
 }
 
+// In-switch reduction of `nvec` vectors at `mc` (multicast address of this rank's shard piece).
+template <typename T>
+__device__ __forceinline__ void nvls_vectors(char* mc, long long nvec, bool avg, int world, Lane ln) {
+    constexpr int U = 4;
+    for (long long v0 = ln.tid; v0 < nvec; v0 += (long long)U * ln.nth) {
+        uint4 raw[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            const long long v = v0 + (long long)k * ln.nth;
+            if (v < nvec) raw[k] = Multimem<T>::ld_reduce(mc + v * FX_VEC_BYTES);
+        }
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            const long long v = v0 + (long long)k * ln.nth;
+            if (v < nvec) multimem_st(mc + v * FX_VEC_BYTES, avg ? scale_vec<T>(raw[k], world) : raw[k]);
+        }
+    }
+}
+
 template <typename T, typename S>
 __global__ void __launch_bounds__(FX_THREADS, 1) k_nvls(const FxLaunch a) {
     const int l = blockIdx.y, b = blockIdx.x;
@@ -615,27 +634,147 @@ __global__ void __launch_bounds__(FX_THREADS, 1) k_nvls(const FxLaunch a) {
     move_all_slices<T, S, true>(m, stage, shard, slice, b, world);
     block_barrier(a, rank, world, b, ++epoch);
     {
-        constexpr int U = 4;
         const long long lo = rank * shard + b * slice;
-        char* mc = a.mc_arena + region + (unsigned long long)lo * sizeof(T);
-        const long long nvec = slice / (FX_VEC_BYTES / (long long)sizeof(T));
-        for (long long v0 = threadIdx.x; v0 < nvec; v0 += (long long)U * FX_THREADS) {
-            uint4 raw[U];
-#pragma unroll
-            for (int k = 0; k < U; ++k) {
-                const long long v = v0 + (long long)k * FX_THREADS;
-                if (v < nvec) raw[k] = Multimem<T>::ld_reduce(mc + v * FX_VEC_BYTES);
-            }
-#pragma unroll
-            for (int k = 0; k < U; ++k) {
-                const long long v = v0 + (long long)k * FX_THREADS;
-                if (v < nvec) multimem_st(mc + v * FX_VEC_BYTES, avg ? scale_vec<T>(raw[k], world) : raw[k]);
-            }
-        }
+        nvls_vectors<T>(a.mc_arena + region + (unsigned long long)lo * sizeof(T),
+                        slice / (FX_VEC_BYTES / (long long)sizeof(T)), avg, world, block_lane());
     }
     block_barrier(a, rank, world, b, ++epoch);
     if (a.mode == FX_MODE_FUSED) move_all_slices<T, S, false>(m, stage, shard, slice, b, world);
     finish_launch(st, pad_of(my), b, epoch, calls);
+}
+
+// ---------------------------------------------------------------------------- pipelined all-reduce
+// The three phases of a sharded all-reduce (pack, reduce, gather/unpack) as three concurrent
+// warp roles of one CTA, decoupled by per-chunk flags instead of CTA-wide barriers:
+//   pack   warps  0-3 : tensors -> own arena, chunk c of slice b of every shard; then
+//                       flagsP[b][me] <- base+c+1 on every peer                        (never waits)
+//   reduce warps 4-11 : wait flagsP[b][*] >= base+c+1; reduce chunk c of slice b of shard `me`
+//                       (multimem through the switch, or pull from the W arenas);
+//                       flagsR[b][me] <- base+c+1 on every peer
+//   gather warps 12-15: wait flagsR[b][*] >= base+c+1; chunk c of slice b of every shard ->
+//                       output tensors (local arena after NVLS, peer arenas on the P2P path)
+// so the NVLink phase of chunk c overlaps the HBM passes of chunks c+1 (pack) and c-1 (unpack),
+// and a cross-GPU flag round trip is paid once at each end instead of once per phase.
+#define FX_PACK_WARPS 4
+#define FX_RED_WARPS 8
+#define FX_UNP_WARPS 4
+
+__device__ __forceinline__ void named_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
+}
+
+// Lane of a thread inside its role, and which slices its warp serves (see slice_lane).
+__device__ __forceinline__ Lane role_slice_lane(int world, int role_warp, int role_warps, int* first, int* step) {
+    const int groups = world < role_warps ? world : role_warps;
+    const int g = role_warp % groups;
+    const int members = role_warps / groups + (g < role_warps % groups ? 1 : 0);
+    *first = g;
+    *step = groups;
+    return Lane{(role_warp / groups) * 32 + (int)(threadIdx.x & 31), members * 32};
+}
+
+enum { FX_FLAG_PACK = 0, FX_FLAG_RED = 1 };
+__device__ __forceinline__ uint32_t* pipe_flag(char* arena, int which, int b, int q) {
+    FxPad* pad = pad_of(arena);
+    return which == FX_FLAG_PACK ? &pad->flags_pack[b][q] : &pad->flags_red[b][q];
+}
+
+__device__ __forceinline__ void signal_peers(const FxLaunch& a, int which, int q, int rank, int b, uint32_t value) {
+    st_release_sys(pipe_flag(a.arena[q], which, b, rank), value);
+}
+
+__device__ __forceinline__ void wait_peer(const FxLaunch& a, int which, int q, int rank, int b, uint32_t value) {
+    const uint32_t* mine = pipe_flag(a.arena[rank], which, b, q);
+    unsigned long long t0 = 0;
+    uint32_t spins = 0;
+    while ((int32_t)(ld_acquire_sys(mine) - value) < 0) {
+        if ((++spins & 0x3ff) == 0) {
+            const unsigned long long now = globaltimer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > a.timeout_ns) {
+                *reinterpret_cast<volatile uint32_t*>(a.status) = (uint32_t)(-FX_ERR_TIMEOUT);
+                __threadfence_system();
+                break;
+            }
+        }
+    }
+}
+
+template <typename T, typename S, bool NVLS, int W, int OP>
+__global__ void __launch_bounds__(FX_THREADS, 1) k_pipe(const FxLaunch a) {
+    const int l = blockIdx.y, b = blockIdx.x;
+    const int rank = a.rank0 + l;
+    const int world = W > 0 ? W : a.world;
+    FxPlanState* st = a.state + l;
+    const uint32_t calls = ld_volatile_u32(&st->calls);
+    const unsigned long long region = a.region[calls & 1];
+    char* my = a.arena[rank];
+    T* stage = reinterpret_cast<T*>(my + region);
+    const uint32_t base = pad_of(my)->pipe_epoch[b];
+    const long long slice = a.slice_elems, shard = a.shard_elems, csz = a.chunk_elems;
+    const int chunks = a.chunks;
+    const bool avg = a.op == FX_AVG;
+    constexpr long long VEC = FX_VEC_BYTES / (long long)sizeof(T);
+    __shared__ MetaSmem meta_smem;
+    const Meta m = load_meta(a, l, &meta_smem);
+
+    const int warp = threadIdx.x >> 5;
+    if (warp < FX_PACK_WARPS) {
+        // ------------------------------------------------ pack role
+        const int rt = threadIdx.x;                                   // thread index inside the role
+        int first, step;
+        const Lane ln = role_slice_lane(world, warp, FX_PACK_WARPS, &first, &step);
+        for (int c = 0; c < chunks; ++c) {
+            const long long c0 = c * csz, c1 = (c0 + csz < slice) ? c0 + csz : slice;
+            for (int s = first; s < world; s += step) {
+                const long long lo = s * shard + b * slice;
+                move_slice<T, S, true>(m, stage, lo + c0, lo + c1, ln);
+            }
+            named_sync(1, FX_PACK_WARPS * 32);
+            if (rt < world) signal_peers(a, FX_FLAG_PACK, rt, rank, b, base + c + 1);
+        }
+    } else if (warp < FX_PACK_WARPS + FX_RED_WARPS) {
+        // ------------------------------------------------ reduce role
+        const int rt = threadIdx.x - FX_PACK_WARPS * 32;
+        const Lane ln{rt, FX_RED_WARPS * 32};
+        for (int c = 0; c < chunks; ++c) {
+            const long long c0 = c * csz, c1 = (c0 + csz < slice) ? c0 + csz : slice;
+            if (rt < world) wait_peer(a, FX_FLAG_PACK, rt, rank, b, base + c + 1);
+            named_sync(2, FX_RED_WARPS * 32);
+            const long long lo = rank * shard + b * slice + c0;
+            const unsigned long long byte_off = region + (unsigned long long)lo * sizeof(T);
+            if (NVLS) nvls_vectors<T>(a.mc_arena + byte_off, (c1 - c0) / VEC, avg, world, ln);
+            else reduce_vectors<T, W, OP>(a, world, byte_off, (c1 - c0) / VEC, avg, my, ln);
+            named_sync(2, FX_RED_WARPS * 32);
+            if (rt < world) signal_peers(a, FX_FLAG_RED, rt, rank, b, base + c + 1);
+        }
+    } else {
+        // ------------------------------------------------ gather / unpack role
+        const int rw = warp - FX_PACK_WARPS - FX_RED_WARPS;
+        const int rt = threadIdx.x - (FX_PACK_WARPS + FX_RED_WARPS) * 32;
+        int first, step;
+        const Lane ln = role_slice_lane(world, rw, FX_UNP_WARPS, &first, &step);
+        for (int c = 0; c < chunks; ++c) {
+            const long long c0 = c * csz, c1 = (c0 + csz < slice) ? c0 + csz : slice;
+            if (rt < world) wait_peer(a, FX_FLAG_RED, rt, rank, b, base + c + 1);
+            named_sync(3, FX_UNP_WARPS * 32);
+            for (int j = first; j < world; j += step) {
+                const int s = (rank + j) % world;
+                const long long lo = s * shard + b * slice;
+                T* from = NVLS ? stage : reinterpret_cast<T*>(a.arena[s] + region);
+                if (a.mode == FX_MODE_FUSED) move_slice<T, S, false>(m, from, lo + c0, lo + c1, ln);
+                else if (!NVLS && s != rank) copy_convert<T, T>(from + lo + c0, stage + lo + c0, c1 - c0, ln);
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        pad_of(my)->pipe_epoch[b] = base + chunks;
+        if (atomicAdd(&st->finished, 1u) == gridDim.x - 1) {
+            st->finished = 0;
+            *reinterpret_cast<volatile uint32_t*>(&st->calls) = calls + 1;
+        }
+    }
 }
 
 __global__ void __launch_bounds__(FX_THREADS, 1) k_barrier(const FxLaunch a) {
@@ -701,7 +840,34 @@ bool fx_kernel_supported(int dtype, int wire, int op, bool broadcast) {
     return op >= FX_SUM && op <= FX_PROD;
 }
 
+template <typename T, typename S>
+int launch_pipe_p2p(fx_plan* plan, const FxLaunch& a, cudaStream_t s) {
+    switch (a.world) {
+        case 2: return launch(k_pipe<T, S, false, 2, FX_SUM>, plan, plan->grid_x, a, s);
+        case 4: return launch(k_pipe<T, S, false, 4, FX_SUM>, plan, plan->grid_x, a, s);
+        case 8: return launch(k_pipe<T, S, false, 8, FX_SUM>, plan, plan->grid_x, a, s);
+    }
+    return launch(k_pipe<T, S, false, 0, FX_SUM>, plan, plan->grid_x, a, s);
+}
+
 int fx_launch_allreduce(fx_plan* plan, const FxLaunch& a, cudaStream_t s) {
+    const bool sum = a.op == FX_SUM || a.op == FX_AVG;
+    if (a.chunks > 0 && sum && plan->algo != FX_ALGO_ONE_SHOT) {          // pipelined kernels
+        const bool nvls = plan->algo == FX_ALGO_NVLS;
+        if (nvls && !a.mc_arena) return fx_fail(FX_ERR_STATE, "NVLS plan without a multicast mapping");
+        if (plan->dtype == FX_F32 && plan->wire == FX_BF16)
+            return nvls ? launch(k_pipe<__nv_bfloat16, float, true, 0, FX_SUM>, plan, plan->grid_x, a, s)
+                        : launch_pipe_p2p<__nv_bfloat16, float>(plan, a, s);
+        switch (plan->wire) {
+            case FX_F32: return nvls ? launch(k_pipe<float, float, true, 0, FX_SUM>, plan, plan->grid_x, a, s)
+                                     : launch_pipe_p2p<float, float>(plan, a, s);
+            case FX_BF16: return nvls ? launch(k_pipe<__nv_bfloat16, __nv_bfloat16, true, 0, FX_SUM>, plan, plan->grid_x, a, s)
+                                      : launch_pipe_p2p<__nv_bfloat16, __nv_bfloat16>(plan, a, s);
+            case FX_F16: return nvls ? launch(k_pipe<__half, __half, true, 0, FX_SUM>, plan, plan->grid_x, a, s)
+                                     : launch_pipe_p2p<__half, __half>(plan, a, s);
+            default: break;                                               // fp64 / ints: classic kernels
+        }
+    }
     if (plan->algo == FX_ALGO_NVLS && (a.op == FX_SUM || a.op == FX_AVG)) {
         if (!a.mc_arena) return fx_fail(FX_ERR_STATE, "NVLS plan without a multicast mapping");
         if (plan->dtype == FX_F32 && plan->wire == FX_BF16) return launch(k_nvls<__nv_bfloat16, float>, plan, plan->grid_x, a, s);
