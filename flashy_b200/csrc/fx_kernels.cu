@@ -38,11 +38,12 @@ __device__ __forceinline__ void st16(void* p, const uint4& v) {
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+__device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t* p) {
     uint32_t v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
 __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
     uint32_t v;
     asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -68,7 +69,8 @@ __device__ __forceinline__ void block_barrier(const FxLaunch& a, int rank, int w
         const uint32_t* mine = &pad_of(a.arena[rank])->flags[b][q];
         unsigned long long t0 = 0;
         uint32_t spins = 0;
-        while ((int32_t)(ld_acquire_sys(mine) - target) < 0) {
+        // poll relaxed (no L1 invalidate per probe), then one acquire fence
+        while ((int32_t)(ld_relaxed_sys(mine) - target) < 0) {
             if ((++spins & 0x3ff) == 0) {
                 const unsigned long long now = globaltimer_ns();
                 if (t0 == 0) t0 = now;
@@ -79,6 +81,7 @@ __device__ __forceinline__ void block_barrier(const FxLaunch& a, int rank, int w
                 }
             }
         }
+        fence_acq_rel_sys();
     }
     __syncthreads();
 }
@@ -424,13 +427,22 @@ __device__ __forceinline__ void reduce_unpack_range(const FxLaunch& a, const Met
             for (int q = 0; q < world; ++q) accumulate<T, OP>(acc, ld16(a.arena[q] + byte_off), q == 0);
         }
         S* dst = static_cast<S*>(m.out[i]) + (e - t0);
+        __align__(16) S vals[VEC];
 #pragma unroll
         for (int k = 0; k < VEC; ++k) {
-            if (k < cnt) {
-                A x = acc[k];
-                if (avg) x = x / static_cast<A>(world);
-                dst[k] = cvt<S, T>(cvt<T, A>(x));              // round to the wire type first: same bits as two-shot
-            }
+            A x = acc[k];
+            if (avg) x = x / static_cast<A>(world);
+            vals[k] = cvt<S, T>(cvt<T, A>(x));                 // round to the wire type first: same bits as two-shot
+        }
+        if (cnt == VEC && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+            constexpr int NS = VEC * sizeof(S) / FX_VEC_BYTES;
+            const uint4* packed = reinterpret_cast<const uint4*>(vals);
+#pragma unroll
+            for (int j = 0; j < NS; ++j) st16(reinterpret_cast<uint4*>(dst) + j, packed[j]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < VEC; ++k)
+                if (k < cnt) dst[k] = vals[k];
         }
     }
 }
@@ -687,7 +699,7 @@ __device__ __forceinline__ void wait_peer(const FxLaunch& a, int which, int q, i
     const uint32_t* mine = pipe_flag(a.arena[rank], which, b, q);
     unsigned long long t0 = 0;
     uint32_t spins = 0;
-    while ((int32_t)(ld_acquire_sys(mine) - value) < 0) {
+    while ((int32_t)(ld_relaxed_sys(mine) - value) < 0) {
         if ((++spins & 0x3ff) == 0) {
             const unsigned long long now = globaltimer_ns();
             if (t0 == 0) t0 = now;
@@ -698,6 +710,7 @@ __device__ __forceinline__ void wait_peer(const FxLaunch& a, int which, int q, i
             }
         }
     }
+    fence_acq_rel_sys();
 }
 
 template <typename T, typename S, bool NVLS, int W, int OP>

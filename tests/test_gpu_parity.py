@@ -479,3 +479,36 @@ def test_count_mismatch_raises_on_every_rank_cuda():
         assert torch.equal(x, torch.ones(5, device="cuda"))
         return raised
     assert run(world, body) == [2] * world
+
+
+@pytest.mark.parametrize("dtype", (torch.bfloat16, torch.float32))
+def test_pipelined_kernel_forced_in_loopback(monkeypatch, dtype):
+    """The warp-role pipelined kernel (default on real multi-GPU buckets) forced on for virtual
+    ranks, with small chunks so that every CTA runs several pipeline stages."""
+    from flashy_b200 import VirtualWorld, distrib
+    import torchvision
+    monkeypatch.setenv("FLASHY_B200_PIPE", "2")
+    monkeypatch.setenv("FLASHY_B200_CHUNK_BYTES", "2048")
+    world = 8
+    numels = [p.numel() for p in torchvision.models.resnet18(num_classes=10).parameters()] + [64] * 40
+    gens = [torch.Generator().manual_seed(300 + r) for r in range(world)]
+    per_rank = [[(torch.randn(n, generator=gens[r]) * 1e-2).to(dtype) for n in numels] for r in range(world)]
+    want = numeric.average_tensors(per_rank)[0]
+    vw = VirtualWorld(world, device=0, arena_mb=256)
+    try:
+        def body(rank, w):
+            ts = [t.cuda() for t in per_rank[rank]]
+            for _ in range(3):
+                cur = [t.clone() for t in ts]
+                distrib.average_tensors(cur)
+            big = torch.full((5 << 20,), float(rank + 1), device="cuda", dtype=dtype)
+            distrib.all_reduce(big)
+            torch.cuda.synchronize()
+            assert torch.equal(big, torch.full_like(big, float(sum(range(1, w + 1)))))
+            return [t.cpu() for t in cur]
+        got = vw.run(body)
+        for r in range(world):
+            for g, w_ in zip(got[r], want):
+                assert torch.equal(g, w_)
+    finally:
+        vw.close()
