@@ -194,6 +194,11 @@ def current() -> BaseContext:
         return _process_ctx
 
 
+import atexit  # noqa: E402
+
+atexit.register(lambda: reset_process_context())
+
+
 def bind(ctx: tp.Optional[BaseContext]) -> None:
     """Make ``ctx`` the context of the calling thread (used for autograd-thread callbacks)."""
     _tls.ctx = ctx

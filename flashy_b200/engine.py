@@ -133,6 +133,15 @@ class Engine:
         dist.barrier()
 
     def close(self) -> None:
+        """Tear the communicator down.  Peers may still be reading this rank's arena in their last
+        kernel, so: finish our own work, wait until every process got here, only then unmap."""
+        if self.comm and not self.host_only:
+            try:
+                torch.cuda.synchronize(self.device)
+                if self.proc_world > 1 and self.n_local == 1:
+                    N.lib.fx_host_barrier(self.comm, 0, 10.0)       # bounded: a dead peer must not hang exit
+            except Exception:      # noqa: BLE001 - best effort at shutdown
+                pass
         with self.lock:
             for plan in self.plans.values():
                 plan.destroy()
