@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--no-graphs", action="store_true", help="eager forward/backward instead of a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=2)
+    ap.add_argument("--kernel-table", default="", help="write a per-kernel device-time table of the timed region (CUPTI) to this file")
     return ap.parse_args()
 
 
@@ -257,7 +258,23 @@ def native_arm(args) -> None:
     cuprof = os.environ.get("FX_BENCH_CUPROF") == "1"                 # ncu --profile-from-start off
     if cuprof:
         torch.cuda.profiler.start()
+    prof = None
+    if args.kernel_table:
+        from torch.profiler import profile, ProfilerActivity
+        prof = profile(activities=[ProfilerActivity.CUDA])
+        prof.__enter__()
     ms_value = timed_region(args.steps, e2e=False)
+    if prof is not None:
+        torch.cuda.synchronize()
+        prof.__exit__(None, None, None)
+        if proc_rank == 0:
+            events = [e for e in prof.key_averages() if e.device_time_total > 0]
+            total = sum(e.device_time_total for e in events)
+            with open(args.kernel_table, "w") as fh:
+                fh.write(f"# kernels of {args.steps} timed steps (torch.profiler / CUPTI), sorted by device time; total {total:.0f} us\n")
+                fh.write("share_pct,device_us,count,name\n")
+                for e in sorted(events, key=lambda e: -e.device_time_total):
+                    fh.write(f"{100 * e.device_time_total / total:.2f},{e.device_time_total:.1f},{e.count},{e.key[:140]}\n")
     if cuprof:
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
