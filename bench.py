@@ -284,6 +284,24 @@ def native_arm(args) -> None:
     # ---- timed: K steps end to end (H2D batch + D2H loss inside the region)
     ms_e2e = timed_region(args.steps, e2e=True)
     clocks = sampler.stop() if sampler else None
+    # ---- auxiliary: one rank alone on this GPU, no sync_model (the W = 1 step of the reference,
+    # where the path is a no-op): what the step costs without any gradient exchange
+    rep0 = replicas[0]
+    torch.cuda.synchronize()
+    with torch.cuda.stream(rep0.stream):
+        for _ in range(3):
+            rep0.graph.replay() if rep0.graph is not None else rep0._fwd_bwd()
+            rep0.optim.step()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(rep0.stream)
+        for _ in range(args.steps):
+            rep0.graph.replay() if rep0.graph is not None else rep0._fwd_bwd()
+            rep0.optim.step()
+            if rep0.graph is None:
+                rep0.optim.zero_grad()
+        s1.record(rep0.stream)
+        rep0.stream.synchronize()
+    single_ms = s0.elapsed_time(s1) / args.steps
 
     if proc_world > 1:
         t = torch.tensor([launches], dtype=torch.float64)
@@ -349,6 +367,10 @@ def native_arm(args) -> None:
         "clocks": clocks,
         "roofline": roofline,
         "allreduce": allreduce,
+        "aux": {"single_rank_no_sync_ms_per_step": single_ms,
+                "single_rank_no_sync_samples_per_s": args.batch / (single_ms * 1e-3),
+                "note": "one replica alone on one GPU without sync_model (the reference's W=1 step); "
+                        "at N=8 (one rank per GPU) ms_per_step minus this is the exposed gradient-sync cost"},
     }
     if n_gpus == 1 and not args.no_cpu_baseline:
         from oracle import cpu_train
