@@ -28,8 +28,8 @@ ALGO_NAMES = {FX_ALGO_ONE_SHOT: "one_shot", FX_ALGO_TWO_SHOT: "two_shot", FX_ALG
 EXPORTS = (
     "fx_last_error", "fx_abi_version", "fx_cuda_available",
     "fx_comm_create", "fx_comm_export", "fx_comm_connect", "fx_comm_enable_multicast",
-    "fx_comm_get_info", "fx_comm_poll", "fx_comm_destroy",
-    "fx_host_exchange", "fx_host_barrier",
+    "fx_comm_get_info", "fx_comm_poll", "fx_comm_abort", "fx_comm_destroy",
+    "fx_host_exchange", "fx_host_barrier", "fx_host_broadcast",
     "fx_plan_create", "fx_plan_get_info", "fx_plan_offsets", "fx_plan_destroy",
     "fx_allreduce", "fx_broadcast", "fx_allreduce_begin", "fx_allreduce_finish", "fx_barrier",
 )
@@ -77,9 +77,11 @@ def _load() -> C.CDLL:
         "fx_comm_enable_multicast": (i, [vp, vp, sz, i]),
         "fx_comm_get_info": (i, [vp, P(CommInfo)]),
         "fx_comm_poll": (i, [vp]),
+        "fx_comm_abort": (i, [vp]),
         "fx_comm_destroy": (None, [vp]),
         "fx_host_exchange": (i, [vp, i, C.c_int64, u64, P(C.c_int64), P(i), C.c_double]),
         "fx_host_barrier": (i, [vp, i, C.c_double]),
+        "fx_host_broadcast": (i, [vp, i, i, vp, sz, C.c_double]),
         "fx_plan_create": (i, [vp, i, P(C.c_int64), i, i, i, i, P(vp)]),
         "fx_plan_get_info": (i, [vp, P(PlanInfo)]),
         "fx_plan_offsets": (i, [vp, P(C.c_int64)]),

@@ -163,6 +163,7 @@ class VirtualWorld:
             except BaseException as err:      # noqa: BLE001
                 errors[local] = err
                 self._barrier.abort()
+                self.engine.abort()           # wake hosted ranks blocked in the native host fabric
             finally:
                 _tls.ctx = None
 
@@ -171,7 +172,8 @@ class VirtualWorld:
             t.start()
         for t in threads:
             t.join()
-        real = [e for e in errors if e is not None and not isinstance(e, threading.BrokenBarrierError)]
+        from ._native import NativeError
+        real = [e for e in errors if e is not None and not isinstance(e, (threading.BrokenBarrierError, NativeError))]
         if real:
             raise real[0]
         broken = [e for e in errors if e is not None]

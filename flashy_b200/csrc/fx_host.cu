@@ -640,6 +640,12 @@ extern "C" int fx_comm_poll(fx_comm* c) {
                    "(ranks issued different collectives, or a rank died)", -(int)s, c->timeout_ns * 1e-9);
 }
 
+extern "C" int fx_comm_abort(fx_comm* c) {
+    if (!c) return fx_fail(FX_ERR_INVALID, "comm is NULL");
+    if (c->shm) c->shm->aborted.store(1, std::memory_order_release);
+    return FX_OK;
+}
+
 extern "C" void fx_comm_destroy(fx_comm* c) {
     if (!c) return;
     c->stop.store(true);
@@ -669,6 +675,8 @@ static int host_wait_all(fx_comm* c, int parity, long long seq, double timeout_s
             if (++spins < 2000) continue;
             sched_yield();
             if ((spins & 0xff) == 0) {
+                if (c->shm->aborted.load(std::memory_order_acquire))
+                    return fx_fail(FX_ERR_STATE, "%s: the communicator was aborted by a rank that failed", what);
                 if (now_s() - t0 > timeout_s)
                     return fx_fail(FX_ERR_TIMEOUT, "%s: rank %d did not arrive within %.0f s (collective #%lld)", what, q, timeout_s, seq);
                 if (spins > 200000) usleep(50);
@@ -682,6 +690,7 @@ extern "C" int fx_host_exchange(fx_comm* c, int local, int64_t count, uint64_t s
                                 int64_t* sum_out, int* sig_equal, double timeout_s) {
     if (!c || local < 0 || local >= c->n_local) return fx_fail(FX_ERR_INVALID, "bad comm/local index");
     if (!c->connected || !c->shm) return fx_fail(FX_ERR_STATE, "communicator is not connected yet");
+    if (c->shm->aborted.load(std::memory_order_acquire)) return fx_fail(FX_ERR_STATE, "the communicator was aborted by a rank that failed");
     if (timeout_s <= 0) timeout_s = env_double("FLASHY_B200_HOST_TIMEOUT", 600.0);
     const int rank = c->rank0 + local;
     const long long seq = ++c->host_seq[local];
@@ -705,6 +714,55 @@ extern "C" int fx_host_exchange(fx_comm* c, int local, int64_t count, uint64_t s
 
 extern "C" int fx_host_barrier(fx_comm* c, int local, double timeout_s) {
     return fx_host_exchange(c, local, 0, 0, nullptr, nullptr, timeout_s);
+}
+
+extern "C" int fx_host_broadcast(fx_comm* c, int local, int src, void* buf, size_t nbytes, double timeout_s) {
+    if (!c || local < 0 || local >= c->n_local) return fx_fail(FX_ERR_INVALID, "bad comm/local index");
+    if (!c->connected || !c->shm) return fx_fail(FX_ERR_STATE, "communicator is not connected yet");
+    if (src < 0 || src >= c->world) return fx_fail(FX_ERR_INVALID, "broadcast source %d out of range", src);
+    if (nbytes && !buf) return fx_fail(FX_ERR_INVALID, "buf is NULL");
+    if (timeout_s <= 0) timeout_s = env_double("FLASHY_B200_HOST_TIMEOUT", 600.0);
+    const int rank = c->rank0 + local;
+    FxShm* sh = c->shm;
+    char* p = static_cast<char*>(buf);
+    const double t0 = now_s();
+    auto spin = [&](auto done, const char* what) -> int {
+        unsigned spins = 0;
+        while (!done()) {
+            if (++spins < 2000) continue;
+            sched_yield();
+            if ((spins & 0xff) == 0) {
+                if (sh->aborted.load(std::memory_order_acquire))
+                    return fx_fail(FX_ERR_STATE, "host broadcast: the communicator was aborted by a rank that failed");
+                if (now_s() - t0 > timeout_s)
+                    return fx_fail(FX_ERR_TIMEOUT, "host broadcast: %s timed out after %.0f s", what, timeout_s);
+            }
+        }
+        return FX_OK;
+    };
+    const size_t rounds = nbytes ? (nbytes + FX_BCAST_CHUNK - 1) / FX_BCAST_CHUNK : 1;
+    for (size_t r = 0; r < rounds; ++r) {
+        const size_t lo = r * FX_BCAST_CHUNK;
+        const size_t n = nbytes > lo ? std::min<size_t>(FX_BCAST_CHUNK, nbytes - lo) : 0;
+        const long long seq = ++c->bcast_seq[local];
+        int rc;
+        if (rank == src) {
+            // the previous chunk must have been consumed by all W-1 readers before it is overwritten
+            if ((rc = spin([&] { return sh->bc_seq.load(std::memory_order_acquire) == seq - 1 &&
+                                        (seq == 1 || sh->bc_acks.load(std::memory_order_acquire) == c->world - 1); },
+                           "waiting for the readers")) != FX_OK) return rc;
+            sh->bc_acks.store(0, std::memory_order_relaxed);
+            if (n) memcpy(sh->bc_data, p + lo, n);
+            sh->bc_len = (long long)n;
+            sh->bc_seq.store(seq, std::memory_order_release);
+        } else {
+            if ((rc = spin([&] { return sh->bc_seq.load(std::memory_order_acquire) == seq; }, "waiting for the source")) != FX_OK) return rc;
+            if ((size_t)sh->bc_len != n) return fx_fail(FX_ERR_MISMATCH, "host broadcast: ranks disagree on the size (%lld vs %zu)", sh->bc_len, n);
+            if (n) memcpy(p + lo, sh->bc_data, n);
+            sh->bc_acks.fetch_add(1, std::memory_order_acq_rel);
+        }
+    }
+    return FX_OK;
 }
 
 // ============================================================================ plans

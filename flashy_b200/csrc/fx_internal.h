@@ -79,9 +79,16 @@ struct FxShmSlot {
     unsigned long long sig;
     long long pad[5];
 };
+#define FX_BCAST_CHUNK (256u << 10)
 struct FxShm {                        // lives in POSIX shared memory (or the heap when single-process)
     FxShmSlot slot[2][FX_MAX_WORLD];
     std::atomic<int> attached;
+    std::atomic<int> aborted;         // set by fx_comm_abort on any rank: every host wait fails
+    // host broadcast channel: the source publishes chunk `bc_seq`, the W-1 readers acknowledge
+    std::atomic<long long> bc_seq;
+    std::atomic<int> bc_acks;
+    long long bc_len;
+    char bc_data[FX_BCAST_CHUNK];
 };
 
 struct fx_comm {
@@ -109,6 +116,7 @@ struct fx_comm {
     bool shm_owner = false, shm_is_heap = false;
     char shm_name[64] = {0};
     long long host_seq[FX_MAX_WORLD] = {0};     // per hosted rank
+    long long bcast_seq[FX_MAX_WORLD] = {0};    // per hosted rank: chunks seen on the broadcast channel
     // fd server (VMM export)
     char sock_name[64] = {0};
     int listen_fd = -1;

@@ -6,8 +6,9 @@ per tensor plus two host-synchronising count checks per ``sync_model``
 (``flashy/distrib.py:78-111``), this module packs each tensor list into a bucket and issues
 ONE kernel of ``libflashy_b200.so`` that reads the peers' staging arenas directly over
 NVLink and fuses the ``/ world_size``.  ``torch.distributed`` is used for bootstrap
-(exchanging memory handles once) and for the two non-tensor utilities ``broadcast_object``
-and ``wrap``; it is never on the per-step path.  There is no CPU / gloo fallback for tensor
+(exchanging memory handles once) and by ``wrap`` (the DDP comparator); ``barrier``,
+``broadcast_object`` and the count check ride the communicator's shared-memory fabric, so after
+bootstrap this module does not touch NCCL/gloo.  There is no CPU / gloo fallback for tensor
 data: CPU tensors in a distributed collective raise.
 
 Environment knobs (none of them changes a public signature):
@@ -725,23 +726,17 @@ def loader(dataset, *args, shuffle=False, klass=DataLoader, **kwargs):
 
 def broadcast_object(obj: tp.Any = None, src: int = 0, device=None):
     """Share a picklable object from rank ``src`` (flashy/distrib.py:246-269).  Every rank,
-    the source included, returns the unpickled copy (as the reference effectively does)."""
+    the source included, returns the unpickled copy (as the reference effectively does).  The
+    pickle travels through the communicator's shared-memory fabric, not ``torch.distributed``."""
     ctx = _context.current()
     if ctx.world == 1:
         return obj
-
-    def lead(payloads):
-        blob = None
-        for r, p in payloads:
-            if r == src:
-                blob = pickle.dumps(p)
-        if distributed.is_initialized() and distributed.get_world_size() > 1:
-            box = [blob]
-            distributed.broadcast_object_list(box, src=src // ctx.n_local)
-            blob = box[0]
-        return blob
-
-    return pickle.loads(ctx.rendezvous((ctx.rank, obj), lead))
+    engine = ctx.cached_engine()
+    if engine is None:
+        engine = ctx.engine_for(torch.cuda.current_device() if N.cuda_available() else None,
+                                host_only=not N.cuda_available())
+    blob = pickle.dumps(obj) if ctx.rank == src else None
+    return pickle.loads(engine.host_broadcast(ctx.local, src, blob))
 
 
 def barrier() -> None:

@@ -160,6 +160,14 @@ class Engine:
     def host_barrier(self, local: int) -> None:
         N.check(N.lib.fx_host_barrier(self.comm, local, 0.0))
 
+    def host_broadcast(self, local: int, src: int, payload: tp.Optional[bytes]) -> bytes:
+        """Bytes from rank ``src`` to every rank over the shared-memory fabric (size first)."""
+        size = C.c_uint64(len(payload) if payload is not None else 0)
+        N.check(N.lib.fx_host_broadcast(self.comm, local, src, C.byref(size), 8, 0.0))
+        buf = C.create_string_buffer(payload, size.value) if payload is not None else C.create_string_buffer(size.value)
+        N.check(N.lib.fx_host_broadcast(self.comm, local, src, buf, size.value, 0.0))
+        return buf.raw[:size.value]
+
     # ------------------------------------------------------------------ planning
     def get_plan(self, kind: str, numels: tp.Tuple[int, ...], dtype: int, wire: int, algo: int = N.FX_ALGO_AUTO) -> Plan:
         if self.host_only:
@@ -241,6 +249,11 @@ class Engine:
                 and self.world >= _env_int("FLASHY_B200_NVLS_MIN_WORLD", 4)):
             return N.FX_ALGO_NVLS
         return N.FX_ALGO_TWO_SHOT
+
+    def abort(self) -> None:
+        """Poison the communicator world-wide: blocked host waits fail instead of hanging."""
+        if self.comm:
+            N.lib.fx_comm_abort(self.comm)
 
     def poll(self) -> None:
         N.check(N.lib.fx_comm_poll(self.comm))

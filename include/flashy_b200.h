@@ -126,6 +126,10 @@ int fx_comm_enable_multicast(fx_comm* comm, const void* blobs, size_t blob_len, 
 int fx_comm_get_info(fx_comm* comm, fx_comm_info* info);
 /* Asynchronous device-side error state (flag-wait timeout): FX_OK or the sticky error. */
 int fx_comm_poll(fx_comm* comm);
+/* Poison the communicator for every rank of the world: all blocked and future host-side
+ * waits (fx_host_exchange / barrier / broadcast) fail with FX_ERR_STATE instead of waiting for
+ * a rank that died.  The communicator cannot be used afterwards (like ncclCommAbort). */
+int fx_comm_abort(fx_comm* comm);
 void fx_comm_destroy(fx_comm* comm);
 
 /* ------------------------------------------------------------------ host-side count check
@@ -139,8 +143,12 @@ void fx_comm_destroy(fx_comm* comm);
  */
 int fx_host_exchange(fx_comm* comm, int local, int64_t count, uint64_t signature,
                      int64_t* sum_out, int* sig_equal, double timeout_s);
-/* Host barrier over the same fabric (used by tests and by distrib.barrier on CUDA-less runs). */
+/* Host barrier over the same fabric.  Replaces torch.distributed.barrier (flashy/distrib.py:276). */
 int fx_host_barrier(fx_comm* comm, int local, double timeout_s);
+/* Copy `nbytes` of host memory from rank `src` to every rank through the shared-memory fabric
+ * (chunked).  Every hosted rank calls it with the same `nbytes`.  Replaces the two
+ * torch.distributed.broadcast calls of broadcast_object (flashy/distrib.py:258,265). */
+int fx_host_broadcast(fx_comm* comm, int local, int src, void* buf, size_t nbytes, double timeout_s);
 
 /* ------------------------------------------------------------------ plans (buckets)
  * A plan is the bucket layout for one ordered tensor list: tensor i of `numels[i]` elements

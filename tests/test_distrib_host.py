@@ -64,6 +64,9 @@ def _worker(rank, world):
     received = distrib.broadcast_object(obj)                       # tests/test_distrib.py:71-79
     assert isinstance(received, defaultdict) and dict(received) == {"test": 42, "youpi": 21}
     assert distrib.broadcast_object(rank * 10, src=world - 1) == (world - 1) * 10
+    big = bytes(range(256)) * 5000 if rank == 1 else None          # 1.28 MB: several fabric chunks
+    assert distrib.broadcast_object(big, src=1) == bytes(range(256)) * 5000
+    assert distrib.broadcast_object(None) is None and distrib.broadcast_object(b"", src=world - 1) == b""
     for _ in range(20):
         distrib.barrier()
 
@@ -126,3 +129,26 @@ def test_virtual_ranks_host_logic():
     finally:
         vw.close()
     assert distrib.world_size() == 1      # outside the virtual world again
+
+
+def _abort_worker(rank, world):
+    """A rank that fails poisons the communicator: the others error out promptly, nobody hangs."""
+    import time
+    from flashy_b200 import distrib, context
+    from flashy_b200._native import NativeError
+    distrib.barrier()                                   # creates the communicator on every rank
+    if rank == 1:
+        context.current().engine.abort()                # what a failing rank does before it dies
+        return
+    t0 = time.time()
+    try:
+        distrib.barrier()
+    except NativeError as err:
+        assert "aborted" in str(err)
+    else:
+        raise AssertionError("the barrier should have failed")
+    assert time.time() - t0 < 30
+
+
+def test_abort_wakes_blocked_ranks():
+    run_ranks(3, "tests.test_distrib_host", "_abort_worker")
