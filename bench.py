@@ -24,8 +24,6 @@ import os
 import statistics
 import subprocess
 import sys
-import threading
-import time
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent

@@ -201,11 +201,6 @@ import atexit  # noqa: E402
 atexit.register(lambda: reset_process_context())
 
 
-def bind(ctx: tp.Optional[BaseContext]) -> None:
-    """Make ``ctx`` the context of the calling thread (used for autograd-thread callbacks)."""
-    _tls.ctx = ctx
-
-
 def reset_process_context() -> None:
     global _process_ctx
     with _process_lock:

@@ -95,12 +95,6 @@ def is_distributed() -> bool:
 # internals
 # ------------------------------------------------------------------------------------------
 
-class _Item(tp.NamedTuple):
-    src: int        # address read by the collective
-    dst: int        # address written (== src for in-place)
-    numel: int      # in fx-dtype units
-
-
 def _is_complex_or_float(tensor: torch.Tensor) -> bool:
     return torch.is_floating_point(tensor) or torch.is_complex(tensor)      # flashy/distrib.py:92-93
 
@@ -605,24 +599,32 @@ def eager_sync_gradients(params: tp.Iterable[torch.Tensor]):
     engine = _engine(ctx, params)
     cap = int(os.environ.get("FLASHY_B200_EAGER_BUCKET_MB", "8")) << 20
 
-    # ---- bucket layout: reverse registration order ~ order in which backward yields grads
-    order = list(range(len(params)))[::-1]
-    layout: tp.List[tp.Tuple[int, tp.List[int]]] = []           # (fx dtype, [param index])
-    for i in order:
-        p = params[i]
-        if p.dtype not in _DTYPES or not p.is_cuda:
-            _flat(p, engine.device)                              # raises with the right message
-        fx, mult = _DTYPES[p.dtype]
-        size = p.numel() * mult * _ESIZE[fx]
-        if layout and layout[-1][0] == fx and sum(params[q].numel() * _DTYPES[params[q].dtype][1] * _ESIZE[fx]
-                                                   for q in layout[-1][1]) + size <= cap:
-            layout[-1][1].append(i)
-        else:
-            layout.append((fx, [i]))
-    where = {}
-    for k, (_, idxs) in enumerate(layout):
-        for j, i in enumerate(idxs):
-            where[i] = (k, j)
+    # ---- bucket layout: reverse registration order ~ order in which backward yields grads.
+    # Cached per parameter list (the entry keeps the parameters alive, so the ids stay unique).
+    cache_key = ("eager", tuple(map(id, params)), cap, engine.wire_bf16)
+    cached = engine.layouts.get(cache_key)
+    if cached is None:
+        layout: tp.List[tp.Tuple[int, tp.List[int]]] = []       # (fx dtype, [param index])
+        fill = 0
+        for i in range(len(params) - 1, -1, -1):
+            p = params[i]
+            if p.dtype not in _DTYPES or not p.is_cuda:
+                _flat(p, engine.device)                          # raises with the right message
+            fx, mult = _DTYPES[p.dtype]
+            size = p.numel() * mult * _ESIZE[fx]
+            if layout and layout[-1][0] == fx and fill + size <= cap:
+                layout[-1][1].append(i)
+                fill += size
+            else:
+                layout.append((fx, [i]))
+                fill = size
+        where = {}
+        for k, (_, idxs) in enumerate(layout):
+            for j, i in enumerate(idxs):
+                where[i] = (k, j)
+        cached = (layout, where, list(params))
+        engine.layouts[cache_key] = cached
+    layout, where, _keepalive = cached
 
     def make_session(_payloads):
         specs = []
