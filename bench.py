@@ -355,6 +355,9 @@ def native_arm(args) -> None:
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": dict(workload_config(args, n_gpus),
                        cuda_graphs=not args.no_graphs,
+                       zero_grad=("implicit: the captured backward starts from grad=None, so every replay overwrites "
+                                  ".grad (same state as zero_grad(set_to_none=True) + backward)" if not args.no_graphs
+                                  else "optim.zero_grad() every step"),
                        l2="not flushed: a step touches weights+grads+activations of every hosted replica "
                           "(> 126 MB L2 at 8 ranks/GPU); the all-reduce kernel streams its bucket once"),
         "e2e": {"value": samples / (ms_e2e * 1e-3), "unit": "samples/s", "ms_per_step": ms_e2e / args.steps,
