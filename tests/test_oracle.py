@@ -163,3 +163,20 @@ def _refdistrib_worker(rank, world):
 def test_refdistrib_matches_reference_bit_for_bit(world):
     """Same backend (gloo) + same call sequence => the restatement reproduces the golden bits."""
     run_ranks(world, "tests.test_oracle", "_refdistrib_worker")
+
+
+def test_bench_reference_arm_line():
+    """`bench.py --impl reference` (CPU, gloo, oracle/refdistrib.py) prints one well-formed JSON line."""
+    import json
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    out = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--world", "2", "--batch", "4"], capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "samples/s" and line["value"] > 0
+    assert line["metric"] == "cifar_resnet18_train_samples_per_sec" and line["higher_is_better"] is True
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["cpu_baseline"]["kind"] == "port"
+    assert line["cpu_baseline"]["cores"] >= 1 and "gloo" in line["cpu_baseline"]["sample"]
