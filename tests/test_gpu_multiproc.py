@@ -108,7 +108,7 @@ def _worker(rank, world, nvls_env="1"):
     import torchvision
     numels = [p.numel() for p in torchvision.models.resnet18(num_classes=10).parameters()]
     for dtype in (torch.bfloat16, torch.float32):
-        for it in range(3):
+        for it in range(2):
             gens = [torch.Generator().manual_seed(1000 + r + 31 * it) for r in range(world)]
             per_rank = [[(torch.randn(n, generator=gens[r]) * 1e-2).to(dtype) for n in numels] for r in range(world)]
             ts = [t.to(dev) for t in per_rank[rank]]
