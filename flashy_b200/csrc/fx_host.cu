@@ -839,13 +839,15 @@ extern "C" int fx_plan_create(fx_comm* c, int world, const int64_t* numels, int 
     p->wire_bytes = (size_t)p->padded * wsize;
     // Pipelined kernel (pack / reduce / gather as concurrent warp roles).  Measured at 8 GPUs: it
     // wins on many-tensor buckets (the per-tensor latency chains of pack and unpack hide behind
-    // the NVLink phase: ResNet-18 bf16 123 -> 110 us) and on flat buffers from ~48 MiB, loses a
-    // few us below that, and loses when all ranks share one GPU (HBM-bound, roles compete).
+    // the NVLink phase: ResNet-18 bf16 123 -> 110 us with NVLS) and on flat buffers from ~48 MiB,
+    // loses a few us below that, and loses when all ranks share one GPU (HBM-bound, roles compete).
     // FLASHY_B200_PIPE: 0 never, 1 auto (default), 2 always.
     const long long pipe_mode = env_ll("FLASHY_B200_PIPE", 1);
     const bool pipe_able = algo != FX_ALGO_ONE_SHOT && dtype != FX_U8 &&
                            (wire_dtype == FX_F32 || wire_dtype == FX_BF16 || wire_dtype == FX_F16);
-    const bool pipe_auto = (n >= 8 || p->wire_bytes >= ((size_t)48 << 20)) && !(c && c->n_local > 1);
+    // (on the peer-to-peer path the roles starve each other: ResNet-18 bf16 137 -> 156 us at W = 8,
+    //  so auto mode pipelines NVLS buckets only)
+    const bool pipe_auto = algo == FX_ALGO_NVLS && (n >= 8 || p->wire_bytes >= ((size_t)48 << 20)) && !(c && c->n_local > 1);
     if (pipe_able && (pipe_mode == 2 || (pipe_mode == 1 && pipe_auto))) {
         const long long chunk_target = env_ll("FLASHY_B200_CHUNK_BYTES", 4096) / (long long)wsize;
         long long chunks = std::max<long long>(1, std::min<long long>(env_ll("FLASHY_B200_MAX_CHUNKS", 8), p->slice / std::max<long long>(chunk_target, slice_align)));
