@@ -203,6 +203,45 @@ class _Layout:
         self.fresh = True
 
 
+def split_buckets(items: tp.Sequence[tp.Tuple[int, int]], cap: int, esize: int
+                  ) -> tp.List[tp.Tuple[tp.List[int], tp.List[int], tp.List[int]]]:
+    """Cut an ordered list of ``(tensor index, numel)`` into buckets of at most ``cap`` elements.
+
+    Returns ``(indices, byte offsets, numels)`` per bucket.  Tensors are never reordered; a
+    tensor larger than ``cap`` is cut into consecutive pieces (byte offset ``piece * cap * esize``
+    into the tensor), each piece a bucket of its own.  Pure function: every rank computes the same
+    split from the same list, which is what keeps the collective sequence identical everywhere."""
+    out: tp.List[tp.Tuple[tp.List[int], tp.List[int], tp.List[int]]] = []
+    idx: tp.List[int] = []
+    off: tp.List[int] = []
+    num: tp.List[int] = []
+    fill = 0
+
+    def flush():
+        nonlocal idx, off, num, fill
+        if idx:
+            out.append((idx, off, num))
+        idx, off, num, fill = [], [], [], 0
+
+    for i, numel in items:
+        if numel > cap:                            # one tensor larger than a bucket: cut it
+            flush()
+            done = 0
+            while done < numel:
+                n = min(cap, numel - done)
+                out.append(([i], [done * esize], [n]))
+                done += n
+            continue
+        if idx and fill + numel > cap:
+            flush()
+        idx.append(i)
+        off.append(0)
+        num.append(numel)
+        fill += numel
+    flush()
+    return out
+
+
 def _build_layout(engine: Engine, kind: str, tensors: tp.Sequence[torch.Tensor], op: int) -> _Layout:
     """Validate the tensors, group them by fx dtype in first-appearance order (identical on
     every rank because the lists are), cut into buckets of at most ``bucket_cap`` wire bytes."""
@@ -220,40 +259,19 @@ def _build_layout(engine: Engine, kind: str, tensors: tp.Sequence[torch.Tensor],
     buckets = []
     for fx, items in groups.items():
         wire = N.FX_BF16 if (engine.wire_bf16 and fx == N.FX_F32 and kind == "ar" and op in (N.FX_AVG, N.FX_SUM)) else fx
-        esize = _ESIZE[fx]
         cap = max(engine.bucket_cap // _ESIZE[wire], 64)
-        cap -= cap % 64
-        cur_idx, cur_off, cur_n, fill = [], [], [], 0
-
-        def flush():
-            nonlocal cur_idx, cur_off, cur_n, fill
-            if cur_idx:
-                plan = engine.get_plan(kind, tuple(cur_n), fx, wire)
-                buckets.append(_Bucket(plan, cur_idx, cur_off))
-            cur_idx, cur_off, cur_n, fill = [], [], [], 0
-
-        for i, numel in items:
-            if numel > cap:                       # one tensor larger than a bucket: cut it
-                flush()
-                done = 0
-                while done < numel:
-                    n = min(cap, numel - done)
-                    cur_idx, cur_off, cur_n = [i], [done * esize], [n]
-                    flush()
-                    done += n
-                continue
-            if cur_idx and fill + numel > cap:
-                flush()
-            cur_idx.append(i)
-            cur_off.append(0)
-            cur_n.append(numel)
-            fill += numel
-        flush()
+        cap -= cap % 64                            # keep cut pieces 128-byte aligned
+        for idx, off, num in split_buckets(items, cap, _ESIZE[fx]):
+            buckets.append(_Bucket(engine.get_plan(kind, tuple(num), fx, wire), idx, off))
     return _Layout(kind, buckets, used)
 
 
-def _dense_or_raise(tensors: tp.Sequence[torch.Tensor]) -> None:
+def _dense_or_raise(tensors: tp.Sequence[torch.Tensor], device: tp.Optional[int] = None) -> None:
+    """Per-call re-validation of a list whose layout is cached (the cache key only covers dtypes
+    and sizes): still CUDA, still on this rank's device, still dense."""
     for t in tensors:
+        if not t.is_cuda or (device is not None and t.device.index != device):
+            _flat(t, -1 if device is None else device)        # raises with the right message
         if not t.is_contiguous() and not _dense(t):
             raise ValueError("Tensors must be contiguous")
 
@@ -317,13 +335,11 @@ def _reduce(ctx, ins: tp.Sequence[torch.Tensor], outs: tp.Optional[tp.Sequence[t
         _flat(ins[0], -1)                          # raises: no CPU fallback
     key = key if key is not None else _list_key(ins)
     layout = _layout_for(ctx, engine, "ar", ins, op, key)
-    _dense_or_raise(ins)
+    _dense_or_raise(ins, engine.device)
     if outs is not None:
         if _list_key(outs) != key:
             raise RuntimeError("output tensors do not match the reduced tensors")
-        _dense_or_raise(outs)
-        for t in outs:
-            _flat(t, engine.device)
+        _dense_or_raise(outs, engine.device)
     in_ptrs = [t.data_ptr() for t in ins]
     _run_layout(ctx, engine, layout, in_ptrs, in_ptrs if outs is None else [t.data_ptr() for t in outs], op)
 
@@ -410,7 +426,7 @@ def broadcast_tensors(tensors: tp.Iterable[torch.Tensor], src: int = 0) -> None:
     if engine.host_only:
         _flat(todo[0], -1)
     layout = _layout_for(ctx, engine, "bc", todo, N.FX_SUM, key)
-    _dense_or_raise(todo)
+    _dense_or_raise(todo, engine.device)
     ptrs = [t.data_ptr() for t in todo]
     _run_layout(ctx, engine, layout, ptrs, ptrs, N.FX_SUM, src)
 
@@ -498,7 +514,7 @@ def _average_cached(ctx, entry: _ModelLists, tag: str, todo: tp.List[torch.Tenso
     if fresh or engine.check_mode != "plan":
         _check_number_of_params(todo, key)
     if ptrs != layout.last_in:
-        _dense_or_raise(todo)
+        _dense_or_raise(todo, engine.device)
     _run_layout(ctx, engine, layout, ptrs, ptrs, N.FX_AVG)
 
 

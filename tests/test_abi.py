@@ -123,3 +123,25 @@ def test_host_only_comm_exchange_single_process(native):
     # a data launch on a host-only communicator must fail loudly
     assert native.lib.fx_barrier(comm, None) == native.FX_ERR_STATE
     native.lib.fx_comm_destroy(comm)
+
+
+def test_bucket_splitting_is_deterministic_and_order_preserving():
+    """flashy_b200.distrib.split_buckets: the host-side cut of a tensor list into launches."""
+    from flashy_b200.distrib import split_buckets
+    items = [(0, 10), (1, 50), (2, 45), (3, 260), (4, 5), (5, 100), (6, 1)]
+    got = split_buckets(items, cap=100, esize=4)
+    assert got == [
+        ([0, 1], [0, 0], [10, 50]),                   # 60 <= 100, next (45) would overflow
+        ([2], [0], [45]),                             # flushed before the oversized tensor
+        ([3], [0], [100]), ([3], [400], [100]), ([3], [800], [60]),   # 260 cut in three, byte offsets
+        ([4], [0], [5]),                              # 5 + 100 would overflow
+        ([5], [0], [100]),                            # exactly one bucket's worth
+        ([6], [0], [1]),
+    ]
+    # every element appears exactly once, in order
+    flat = [(i, o, n) for idx, off, num in got for i, o, n in zip(idx, off, num)]
+    assert [i for i, _, _ in flat] == sorted(i for i, _, _ in flat)
+    for i, numel in items:
+        assert sum(n for j, _, n in flat if j == i) == numel
+    assert split_buckets([], 100, 4) == []
+    assert split_buckets([(0, 100)], 100, 2) == [([0], [0], [100])]
