@@ -89,7 +89,7 @@ class ClockSampler:
         self.proc = None
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", f"--id={index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             pass
@@ -281,7 +281,17 @@ def native_arm(args) -> None:
     timings = list(eng.timings)
     # ---- timed: K steps end to end (H2D batch + D2H loss inside the region)
     ms_e2e = timed_region(args.steps, e2e=True)
+    # The timed regions are short (tens of ms at 8 GPUs): keep the same load running until the
+    # sampler has had ~0.6 s, so that the median SM clock under load rests on enough samples.
+    # Collective: every rank runs the same number of extra (untimed) steps.
+    t_load = ms_value + ms_e2e
+    extra = 0
+    while t_load < 600.0 and extra < 40:
+        t_load += timed_region(args.steps, e2e=False)
+        extra += 1
     clocks = sampler.stop() if sampler else None
+    if clocks is not None:
+        clocks["sampled_over_ms"] = t_load
     # ---- auxiliary: one rank alone on this GPU, no sync_model (the W = 1 step of the reference,
     # where the path is a no-op): what the step costs without any gradient exchange
     rep0 = replicas[0]
