@@ -331,7 +331,7 @@ extern "C" int fx_comm_create(int world, int rank0, int n_local, int device, siz
     if (!c) return fx_fail(FX_ERR_SYS, "out of memory");
     c->world = world; c->rank0 = rank0; c->n_local = n_local; c->device = device; c->flags = flags;
     c->host_only = (flags & FX_COMM_HOST_ONLY) != 0;
-    c->timeout_ns = (unsigned long long)(env_double("FLASHY_B200_DEVICE_TIMEOUT", 30.0) * 1e9);
+    c->timeout_ns = (unsigned long long)(env_double("FLASHY_B200_DEVICE_TIMEOUT", 120.0) * 1e9);
     srand((unsigned)(getpid() * 2654435761u) ^ (unsigned)time(nullptr));
     const unsigned nonce = (unsigned)rand();
 
