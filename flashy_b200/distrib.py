@@ -363,7 +363,14 @@ def all_reduce(tensor: torch.Tensor, op=distributed.ReduceOp.SUM):
     fx_op = _OPS.get(op)
     if fx_op is None:
         raise RuntimeError(f"reduce op {op} is not supported by flashy_b200")
-    _reduce(ctx, [tensor], None, fx_op)
+    # Host rendezvous first (a few microseconds in shared memory): a rank that is late -- rank 0
+    # writing a checkpoint, say -- is waited for on the host, not by GPUs spinning on flags, and
+    # ranks that disagree on the tensor's size are refused instead of corrupting each other.
+    key = _list_key([tensor])
+    engine = _engine(ctx, [tensor])
+    if not (engine.check_mode == "plan" and ("ar", key, engine.wire_bf16 and fx_op in (N.FX_AVG, N.FX_SUM)) in engine.layouts):
+        _check_number_of_params([tensor], key)
+    _reduce(ctx, [tensor], None, fx_op, key)
     return None
 
 
