@@ -631,6 +631,16 @@ extern "C" int fx_comm_get_info(fx_comm* c, fx_comm_info* info) {
     return FX_OK;
 }
 
+extern "C" int fx_comm_get_pointers(fx_comm* c, void** arenas, void** mc_base, uint64_t* mc_bytes, uint64_t* pad_bytes) {
+    if (!c) return fx_fail(FX_ERR_INVALID, "comm is NULL");
+    if (c->host_only || !c->connected) return fx_fail(FX_ERR_STATE, "needs a connected device communicator");
+    if (arenas) for (int r = 0; r < c->world; ++r) arenas[r] = c->arena[r].base;
+    if (mc_base) *mc_base = c->mc_base;
+    if (mc_bytes) *mc_bytes = c->multicast ? c->mc_bytes : 0;
+    if (pad_bytes) *pad_bytes = FX_PAD_BYTES;
+    return FX_OK;
+}
+
 extern "C" int fx_comm_poll(fx_comm* c) {
     if (!c) return fx_fail(FX_ERR_INVALID, "comm is NULL");
     if (c->host_only || !c->status_host) return FX_OK;
@@ -656,6 +666,7 @@ extern "C" void fx_comm_destroy(fx_comm* c) {
         cudaDeviceSynchronize();
         for (int r = 0; r < c->world; ++r) arena_release(c, c->arena[r]);
         if (c->status_host) cudaFreeHost(c->status_host);
+        if (c->order_event) cudaEventDestroy(c->order_event);
         cudaGetLastError();
     }
     if (c->shm) {
@@ -1002,12 +1013,38 @@ static int upload_ptrs(void** dst, std::vector<const void*>* shadow_c, std::vect
     return FX_OK;
 }
 
+// All collective kernels of a communicator share one signal pad (flags, epochs), so two of them
+// must never be in flight at once.  Launches on ONE stream are ordered by the stream; when the
+// launch stream changes (eager buckets on the side stream, then a collective on the user's stream)
+// the new stream is made to wait for everything the previous launch stream holds.  Inside a stream
+// capture the caller orders the launches itself (fork / join of the side stream).
+static int order_after_previous(fx_comm* c, cudaStream_t stream) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess) { cudaGetLastError(); return FX_OK; }
+    if (cap != cudaStreamCaptureStatusNone) return FX_OK;
+    if (c->have_last && c->last_stream != (void*)stream) {
+        cudaStream_t prev = static_cast<cudaStream_t>(c->last_stream);
+        cudaStreamCaptureStatus pcap = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(prev, &pcap) != cudaSuccess || pcap != cudaStreamCaptureStatusNone) {
+            cudaGetLastError();
+        } else {
+            if (!c->order_event) FX_CUDA(cudaEventCreateWithFlags(&c->order_event, cudaEventDisableTiming));
+            if (cudaEventRecord(c->order_event, prev) == cudaSuccess) FX_CUDA(cudaStreamWaitEvent(stream, c->order_event, 0));
+            else cudaGetLastError();                       // the previous stream no longer exists
+        }
+    }
+    c->last_stream = (void*)stream;
+    c->have_last = true;
+    return FX_OK;
+}
+
 static int pre_launch(fx_comm* c, fx_plan* p, cudaStream_t stream) {
     if (!c || c->host_only) return fx_fail(FX_ERR_STATE, "this communicator has no device side");
     if (!c->connected) return fx_fail(FX_ERR_STATE, "communicator is not connected yet");
     int rc = fx_comm_poll(c);
     if (rc != FX_OK) return rc;
     FX_CUDA(cudaSetDevice(c->device));
+    if ((rc = order_after_previous(c, stream)) != FX_OK) return rc;
     if (p && p->recycled) {          // its arena region was used by a destroyed plan: fence the old readers
         FxLaunch a;
         fill_launch(c, nullptr, a);
@@ -1044,6 +1081,8 @@ extern "C" int fx_allreduce_begin(fx_plan* p, int op, const void* const* in_ptrs
     fx_comm* c = p->comm;
     if (!c) return fx_fail(FX_ERR_STATE, "dry plan cannot be launched");
     if (p->algo == FX_ALGO_ONE_SHOT) return fx_fail(FX_ERR_INVALID, "begin/finish needs a sharded (TWO_SHOT / NVLS) plan");
+    if (p->begun) return fx_fail(FX_ERR_STATE, "fx_allreduce_begin on a plan whose previous begin has no matching finish yet "
+                                               "(a plan owns one pair of staging regions: use one plan per bucket in flight)");
     if (!fx_kernel_supported(p->dtype, p->wire, op, false)) return fx_fail(FX_ERR_UNSUPPORTED, "all-reduce op %d on dtype %d is not supported", op, p->dtype);
     std::lock_guard<std::mutex> lock(c->mu);
     cudaStream_t s = static_cast<cudaStream_t>(stream);

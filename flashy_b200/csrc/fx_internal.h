@@ -123,8 +123,9 @@ struct fx_comm {
     std::thread server;
     std::atomic<bool> stop{false};
     std::mutex mu;
-    void* last_stream = nullptr;
-    bool need_barrier_before_next = false;
+    void* last_stream = nullptr;      // stream of the most recent collective launch (see order_after_previous)
+    bool have_last = false;
+    cudaEvent_t order_event = nullptr;
 };
 
 struct fx_plan {

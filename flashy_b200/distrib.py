@@ -242,9 +242,10 @@ def split_buckets(items: tp.Sequence[tp.Tuple[int, int]], cap: int, esize: int
     return out
 
 
-def _build_layout(engine: Engine, kind: str, tensors: tp.Sequence[torch.Tensor], op: int) -> _Layout:
+def _build_layout(engine: Engine, kind: str, tensors: tp.Sequence[torch.Tensor], op: int, lossy: bool = False) -> _Layout:
     """Validate the tensors, group them by fx dtype in first-appearance order (identical on
-    every rank because the lists are), cut into buckets of at most ``bucket_cap`` wire bytes."""
+    every rank because the lists are), cut into buckets of at most ``bucket_cap`` wire bytes.
+    ``lossy``: the caller is a gradient-averaging path, where ``FLASHY_B200_WIRE=bf16`` may apply."""
     groups: tp.Dict[int, tp.List[tp.Tuple[int, int]]] = {}
     used = []
     for i, t in enumerate(tensors):
@@ -258,7 +259,7 @@ def _build_layout(engine: Engine, kind: str, tensors: tp.Sequence[torch.Tensor],
             groups.setdefault(fx, []).append((i, numel))
     buckets = []
     for fx, items in groups.items():
-        wire = N.FX_BF16 if (engine.wire_bf16 and fx == N.FX_F32 and kind == "ar" and op in (N.FX_AVG, N.FX_SUM)) else fx
+        wire = N.FX_BF16 if (lossy and engine.wire_bf16 and fx == N.FX_F32 and kind == "ar" and op == N.FX_AVG) else fx
         cap = max(engine.bucket_cap // _ESIZE[wire], 64)
         cap -= cap % 64                            # keep cut pieces 128-byte aligned
         for idx, off, num in split_buckets(items, cap, _ESIZE[fx]):
@@ -315,12 +316,13 @@ def _run_layout(ctx, engine: Engine, layout: _Layout, in_ptrs: tp.List[int],
             torch.cuda.current_stream().wait_event(done)
 
 
-def _layout_for(ctx, engine: Engine, kind: str, tensors: tp.Sequence[torch.Tensor], op: int, key) -> _Layout:
-    full = (kind, key, engine.wire_bf16 and op in (N.FX_AVG, N.FX_SUM))
+def _layout_for(ctx, engine: Engine, kind: str, tensors: tp.Sequence[torch.Tensor], op: int, key,
+                lossy: bool = False) -> _Layout:
+    full = (kind, key, lossy and engine.wire_bf16 and op == N.FX_AVG)
     layout = engine.layouts.get(full)
     if layout is None or any(b.plan.handle is None for b in layout.buckets):
         for _ in range(2):       # an arena eviction while building invalidates earlier buckets: redo once
-            layout = _build_layout(engine, kind, tensors, op)
+            layout = _build_layout(engine, kind, tensors, op, lossy)
             if all(b.plan.handle is not None for b in layout.buckets):
                 break
         engine.layouts[full] = layout
@@ -328,13 +330,13 @@ def _layout_for(ctx, engine: Engine, kind: str, tensors: tp.Sequence[torch.Tenso
 
 
 def _reduce(ctx, ins: tp.Sequence[torch.Tensor], outs: tp.Optional[tp.Sequence[torch.Tensor]], op: int,
-            key=None) -> None:
+            key=None, lossy: bool = False) -> None:
     """Bucketed all-reduce of ``ins`` (into ``outs`` if given, else in place)."""
     engine = _engine(ctx, ins)
     if engine.host_only:
         _flat(ins[0], -1)                          # raises: no CPU fallback
     key = key if key is not None else _list_key(ins)
-    layout = _layout_for(ctx, engine, "ar", ins, op, key)
+    layout = _layout_for(ctx, engine, "ar", ins, op, key, lossy)
     _dense_or_raise(ins, engine.device)
     if outs is not None:
         if _list_key(outs) != key:
@@ -368,7 +370,7 @@ def all_reduce(tensor: torch.Tensor, op=distributed.ReduceOp.SUM):
     # ranks that disagree on the tensor's size are refused instead of corrupting each other.
     key = _list_key([tensor])
     engine = _engine(ctx, [tensor])
-    if not (engine.check_mode == "plan" and ("ar", key, engine.wire_bf16 and fx_op in (N.FX_AVG, N.FX_SUM)) in engine.layouts):
+    if not (engine.check_mode == "plan" and ("ar", key, False) in engine.layouts):
         _check_number_of_params([tensor], key)
     _reduce(ctx, [tensor], None, fx_op, key)
     return None
@@ -396,15 +398,43 @@ def wrap(model):
     return model
 
 
+class _ListEntry:
+    """Remembered validation of one tensor list: what a repeat call must still match."""
+    __slots__ = ("numels", "dtypes", "key", "layout")
+
+    def __init__(self, numels, dtypes, key, layout):
+        self.numels, self.dtypes, self.key, self.layout = numels, dtypes, key, layout
+
+
 def _average(ctx, todo: tp.List[torch.Tensor]) -> None:
-    """Count check + bucketed in-place mean of an already filtered list."""
-    key = _list_key(todo)
+    """Count check + bucketed in-place mean of an already filtered list.
+
+    Repeat calls with a list of the same length, element counts and dtypes (the per-step
+    ``sync_gradients`` / ``average_tensors`` pattern) skip the key building, the layout lookup and
+    the density re-validation: three list passes instead of eight."""
     engine = _engine(ctx, todo)
-    full = ("ar", key, engine.wire_bf16)
-    known = full in engine.layouts
+    numels = [t.numel() for t in todo]
+    slot = (len(todo), numels[0], numels[-1], engine.wire_bf16)
+    ent = engine.fast_lists.get(slot)
+    if ent is not None and ent.numels == numels and ent.dtypes == [t.dtype for t in todo] \
+            and all(b.plan.handle is not None for b in ent.layout.buckets):
+        key, layout, known = ent.key, ent.layout, True
+    else:
+        key = _list_key(todo)
+        known = ("ar", key, engine.wire_bf16) in engine.layouts
+        if engine.host_only:
+            _check_number_of_params(todo, key)
+            _flat(todo[0], -1)                     # raises: no CPU fallback
+        layout = _layout_for(ctx, engine, "ar", todo, N.FX_AVG, key, lossy=True)
+        engine.fast_lists[slot] = _ListEntry(numels, [t.dtype for t in todo], key, layout)
+        if len(engine.fast_lists) > 64:
+            engine.fast_lists.pop(next(iter(engine.fast_lists)))
     if not (known and engine.check_mode == "plan"):
         _check_number_of_params(todo, key)
-    _reduce(ctx, todo, None, N.FX_AVG, key)
+    ptrs = [t.data_ptr() for t in todo]
+    if ptrs != layout.last_in:
+        _dense_or_raise(todo, engine.device)
+    _run_layout(ctx, engine, layout, ptrs, ptrs, N.FX_AVG)
 
 
 def average_tensors(tensors: tp.Iterable[torch.Tensor]) -> None:
@@ -466,26 +496,45 @@ def sync_buffers(model: torch.nn.Module, average: bool = True) -> None:
 
 
 class _ModelLists:
-    __slots__ = ("params", "buffers", "float_buffers", "age", "fast")
+    __slots__ = ("params", "buffers", "float_buffers", "age", "fast", "epoch")
 
     def __init__(self, model):
         self.params = list(model.parameters())
         self.buffers = list(model.buffers())
         self.float_buffers = [b for b in self.buffers if b.dtype.is_floating_point or b.dtype.is_complex]
         self.age = 0
+        self.epoch = _struct_epoch[0]
         self.fast: tp.Dict[tp.Any, tp.Any] = {}     # (tag, n) -> (key, layout) of a validated tensor list
 
 
 _model_cache: "weakref.WeakKeyDictionary[torch.nn.Module, _ModelLists]" = weakref.WeakKeyDictionary()
 _MODEL_REVALIDATE = 256
 
+# Structural edits of ANY module (``model.fc = nn.Linear(...)``, ``register_parameter``,
+# ``register_buffer``, ``add_module``, assigning ``None`` over a child) go through torch's global
+# registration hooks: they bump this counter, and a cached parameter list taken at an older count
+# is thrown away on its next use.  The reference walks the module tree on every call
+# (flashy/distrib.py:205-210); this keeps that behaviour observable at O(1) per call.
+_struct_epoch = [0]
+
+
+def _bump_struct_epoch(*_args) -> None:
+    _struct_epoch[0] += 1
+
+
+torch.nn.modules.module.register_module_parameter_registration_hook(_bump_struct_epoch)
+torch.nn.modules.module.register_module_module_registration_hook(_bump_struct_epoch)
+torch.nn.modules.module.register_module_buffer_registration_hook(_bump_struct_epoch)
+
 
 def _model_entry(model: torch.nn.Module) -> _ModelLists:
     """``list(model.parameters())`` / ``list(model.buffers())`` walk the whole module tree on
     every call (~100 us for ResNet-18 -- more than the all-reduce itself takes on NVLink), so
-    the lists are cached per model and re-derived every 256 uses to pick up structural edits."""
+    the lists are cached per model.  The cache is dropped whenever any module's structure was
+    edited since it was taken (``_struct_epoch``), and re-derived every 256 uses as a backstop for
+    edits that bypass the registration API (``del model.fc``, writes to ``_parameters``)."""
     entry = _model_cache.get(model)
-    if entry is None or entry.age >= _MODEL_REVALIDATE:
+    if entry is None or entry.epoch != _struct_epoch[0] or entry.age >= _MODEL_REVALIDATE:
         entry = _ModelLists(model)
         _model_cache[model] = entry
     entry.age += 1
@@ -515,7 +564,7 @@ def _average_cached(ctx, entry: _ModelLists, tag: str, todo: tp.List[torch.Tenso
         if engine.host_only:
             _check_number_of_params(todo, key)
             _flat(todo[0], -1)
-        layout = _layout_for(ctx, engine, "ar", todo, N.FX_AVG, key)
+        layout = _layout_for(ctx, engine, "ar", todo, N.FX_AVG, key, lossy=True)
         entry.fast[slot] = (key, layout)
         fresh = True
     if fresh or engine.check_mode != "plan":
@@ -647,6 +696,9 @@ def eager_sync_gradients(params: tp.Iterable[torch.Tensor]):
                 where[i] = (k, j)
         cached = (layout, where, list(params))
         engine.layouts[cache_key] = cached
+        stale = [k for k in engine.layouts if isinstance(k, tuple) and k and k[0] == "eager"]
+        for k in stale[:-8]:                                     # the entries pin their parameters: keep a few
+            del engine.layouts[k]
     layout, where, _keepalive = cached
 
     def make_session(_payloads):
@@ -655,7 +707,10 @@ def eager_sync_gradients(params: tp.Iterable[torch.Tensor]):
             numels = tuple(params[i].numel() * _DTYPES[params[i].dtype][1] for i in idxs)
             wire = N.FX_BF16 if (engine.wire_bf16 and fx == N.FX_F32) else fx
             algo = engine.sharded_algo(wire, sum(numels) * _ESIZE[wire])
-            specs.append((engine.get_plan("ar", numels, fx, wire, algo), len(idxs)))
+            # tag = bucket index: two buckets of identical shape (e.g. the three 512x512x3x3 convolutions
+            # of ResNet-18's layer4 with a small bucket cap) must not share one plan -- a plan has ONE
+            # pair of staging regions and one call counter, and all begins precede all finishes.
+            specs.append((engine.get_plan("ar", numels, fx, wire, algo, tag=("eager", len(specs))), len(idxs)))
         return _EagerSession(engine, ctx.n_local, specs)
 
     session: _EagerSession = ctx.rendezvous(None, make_session)
@@ -720,7 +775,7 @@ def eager_sync_gradients(params: tp.Iterable[torch.Tensor]):
                 if got:
                     for i in got:
                         assert params[i].grad is not None
-                    _reduce(ctx, [fired[i] for i in got], [params[i].grad.data for i in got], N.FX_AVG)
+                    _reduce(ctx, [fired[i] for i in got], [params[i].grad.data for i in got], N.FX_AVG, lossy=True)
         fired.clear()
 
 

@@ -93,6 +93,7 @@ class Engine:
         self.wire_bf16 = os.environ.get("FLASHY_B200_WIRE", "") == "bf16"
         self.side_stream = None if self.host_only else torch.cuda.Stream(device=self.device)
         self.layouts: tp.Dict[tp.Any, tp.Any] = {}       # bucket layouts of tensor lists (distrib.py)
+        self.fast_lists: tp.Dict[tp.Any, tp.Any] = {}    # validated repeat lists of average_tensors (distrib.py)
         self.multicast = bool(self.info.multicast)
         self.nvls_min = _env_int("FLASHY_B200_NVLS_MIN", 512 << 10)
         self.profile = False
@@ -169,10 +170,13 @@ class Engine:
         return buf.raw[:size.value]
 
     # ------------------------------------------------------------------ planning
-    def get_plan(self, kind: str, numels: tp.Tuple[int, ...], dtype: int, wire: int, algo: int = N.FX_ALGO_AUTO) -> Plan:
+    def get_plan(self, kind: str, numels: tp.Tuple[int, ...], dtype: int, wire: int, algo: int = N.FX_ALGO_AUTO,
+                 tag: tp.Any = None) -> Plan:
+        """Cached plan of one bucket.  ``tag`` distinguishes plans of identical shape that must not
+        share staging memory (several begin/finish buckets in flight at once)."""
         if self.host_only:
             raise RuntimeError("flashy_b200: no CUDA device in this process; tensor collectives have no CPU fallback")
-        key = (kind, numels, dtype, wire, algo)
+        key = (kind, numels, dtype, wire, algo) if tag is None else (kind, numels, dtype, wire, algo, tag)
         with self.lock:
             plan = self.plans.get(key)
             if plan is not None:
@@ -189,6 +193,7 @@ class Engine:
                     old.destroy()
                 self.plans.clear()
                 self.layouts.clear()
+                self.fast_lists.clear()
                 plan = Plan(self, key, numels, dtype, wire, algo)
             self.plans[key] = plan
             return plan

@@ -124,6 +124,12 @@ int fx_comm_connect(fx_comm* comm, const void* blobs, size_t blob_len, int n_pro
  * device, driver or allocation kind cannot do it; the P2P algorithms keep working. */
 int fx_comm_enable_multicast(fx_comm* comm, const void* blobs, size_t blob_len, int n_procs);
 int fx_comm_get_info(fx_comm* comm, fx_comm_info* info);
+/* Diagnostics / benchmarks: the arena base of every rank as mapped in this process
+ * (`arenas[world]`, staging starts `pad_bytes` in), and the NVSwitch multicast alias of the
+ * arenas (`mc_base` NULL / `mc_bytes` 0 without NVLS).  No reference counterpart: this is
+ * the window the micro-benchmarks under benchmarks/ use to time raw NVLink / multimem rates. */
+int fx_comm_get_pointers(fx_comm* comm, void** arenas, void** mc_base, uint64_t* mc_bytes,
+                         uint64_t* pad_bytes);
 /* Asynchronous device-side error state (flag-wait timeout): FX_OK or the sticky error. */
 int fx_comm_poll(fx_comm* comm);
 /* Poison the communicator for every rank of the world: all blocked and future host-side
