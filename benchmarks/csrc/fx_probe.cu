@@ -71,6 +71,7 @@ __device__ __forceinline__ void mm_red_release(uint32_t* p, uint32_t v) {
     asm volatile("multimem.red.release.sys.global.add.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void fence_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+__device__ __forceinline__ void fence_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ unsigned long long gtimer() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -316,7 +317,22 @@ __global__ void k_latency(const ProbeArgs a) {
     for (int i = 0; i < a.iters; ++i) fence_sys();
     t1 = gtimer();
     a.out[6] = (t1 - t0) / a.iters;
-    a.out[7] = acc;
+    // 7: gpu-scope fence alone   8: local store + gpu fence   9: multimem.st + gpu fence
+    t0 = gtimer();
+    for (int i = 0; i < a.iters; ++i) fence_gpu();
+    t1 = gtimer();
+    a.out[7] = (t1 - t0) / a.iters;
+    t0 = gtimer();
+    for (int i = 0; i < a.iters; ++i) { st16(a.arena[a.rank] + off + (size_t)i * 65536, make_uint4(0, 0, 0, 0)); fence_gpu(); }
+    t1 = gtimer();
+    a.out[8] = (t1 - t0) / a.iters;
+    if (a.mc) {
+        t0 = gtimer();
+        for (int i = 0; i < a.iters; ++i) { mm_st(a.mc + off + (size_t)i * 65536, make_uint4(0, 0, 0, 0)); fence_gpu(); }
+        t1 = gtimer();
+        a.out[9] = (t1 - t0) / a.iters;
+    }
+    a.out[15] = acc;
 }
 
 // ---------------------------------------------------------------- barrier probes
@@ -344,6 +360,15 @@ __global__ void k_barrier_probe(const ProbeArgs a) {
                 mm_red_release(ctr, 1u);
                 const uint32_t want = epoch * (uint32_t)a.world;                           // epoch0 starts at 0 for this variant
                 while ((int32_t)(ld_acquire_sys(mine + 64) - want) < 0) {}
+            }
+        } else if (VARIANT == 3) {
+            if (threadIdx.x == 0) fence_gpu();
+            __syncthreads();
+            if ((int)threadIdx.x < a.world) {
+                const int q = threadIdx.x;
+                st_relaxed_sys(reinterpret_cast<uint32_t*>(a.arena[q] + a.flags_off) + 192 + a.rank, epoch);
+                while ((int32_t)(ld_relaxed_sys(mine + 192 + q) - epoch) < 0) {}
+                fence_gpu();
             }
         } else {
             if (threadIdx.x == 0) fence_sys();
@@ -392,6 +417,7 @@ extern "C" int fxp_mix(int grid, int threads, int unroll, int copy_unroll, const
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (copy_unroll != 8) return -1;
     switch (unroll) {
+        case 1: k_mix<1, 8><<<grid, threads, 0, s>>>(*a); break;
         case 2: k_mix<2, 8><<<grid, threads, 0, s>>>(*a); break;
         case 4: k_mix<4, 8><<<grid, threads, 0, s>>>(*a); break;
         case 8: k_mix<8, 8><<<grid, threads, 0, s>>>(*a); break;
@@ -405,12 +431,14 @@ extern "C" int fxp_mix_tma(int grid, int threads, int unroll, const ProbeArgs* a
     const int smem = TMA_STAGES * TMA_TILE + 64;
     static bool attr = false;
     if (!attr) {
+        cudaFuncSetAttribute(k_mix_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         cudaFuncSetAttribute(k_mix_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         cudaFuncSetAttribute(k_mix_tma<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         cudaFuncSetAttribute(k_mix_tma<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         attr = true;
     }
     switch (unroll) {
+        case 1: k_mix_tma<1><<<grid, threads, smem, s>>>(*a); break;
         case 2: k_mix_tma<2><<<grid, threads, smem, s>>>(*a); break;
         case 4: k_mix_tma<4><<<grid, threads, smem, s>>>(*a); break;
         case 8: k_mix_tma<8><<<grid, threads, smem, s>>>(*a); break;
@@ -430,6 +458,7 @@ extern "C" int fxp_barrier(int variant, const ProbeArgs* a, void* stream) {
         case 0: k_barrier_probe<0><<<1, 64, 0, s>>>(*a); break;
         case 1: k_barrier_probe<1><<<1, 64, 0, s>>>(*a); break;
         case 2: k_barrier_probe<2><<<1, 64, 0, s>>>(*a); break;
+        case 3: k_barrier_probe<3><<<1, 64, 0, s>>>(*a); break;
         default: return -1;
     }
     return cudaGetLastError() == cudaSuccess ? 0 : -2;

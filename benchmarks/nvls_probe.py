@@ -159,8 +159,8 @@ def main():
 
     sptr = C.c_void_p(stream.cuda_stream)
     grids = [16, 32, 64, 148, 296] if not args.quick else [32, 148]
-    threads_l = [256, 512, 1024] if not args.quick else [512]
-    unrolls = [2, 4, 8, 16] if not args.quick else [4, 8]
+    threads_l = [64, 128, 256, 512, 1024] if not args.quick else [512]
+    unrolls = [1, 2, 4, 8, 16] if not args.quick else [4, 8]
     mode_names = {0: "ld_reduce+mc_st", 1: "ld_reduce+local_st", 2: "mc_st", 3: "p2p_pull", 4: "ld_reduce+mc_st(swp)",
                   5: "local_copy", 6: "ld_reduce_bf16+mc_st"}
     modes = [0, 4, 1, 2, 6, 3] if have_mc else ([3] if world > 1 else [])
@@ -169,8 +169,10 @@ def main():
             for grid in grids:
                 for threads in threads_l:
                     for u in unrolls:
-                        if mode not in (0, 4) and (pattern == 0 or threads == 1024 or u == 16 or grid == 16):
+                        if mode != 0 and (pattern == 0 or threads in (64, 1024) or u in (1, 16) or grid == 16):
                             continue        # the full grid only for the all-reduce core
+                        if mode == 0 and pattern == 0 and (threads in (64, 1024) or u in (1, 16)):
+                            continue
                         a = mkargs(pattern=pattern)
                         timed(dict(kind="mm", mode=mode_names[mode], grid=grid, threads=threads, unroll=u, pattern=pattern),
                               lambda: probe.fxp_mm(mode, grid, threads, u, C.byref(a), sptr))
@@ -186,13 +188,13 @@ def main():
     if have_mc:
         # reduce role + copy role in one CTA
         for grid in (148, 296):
-            for tr, tc in ((256, 256), (384, 128), (512, 256), (512, 512), (768, 256)):
-                for u in (4, 8):
+            for tr, tc in ((64, 256), (128, 256), (256, 256), (384, 128), (512, 256), (512, 512), (768, 256)):
+                for u in (1, 2, 4, 8):
                     a = mkargs(pattern=1, reduce_threads=tr)
                     timed(dict(kind="mix", how="registers", grid=grid, reduce_threads=tr, copy_threads=tc, unroll=u),
                           lambda: probe.fxp_mix(grid, tr + tc, u, 8, C.byref(a), sptr))
-            for tr in (256, 512, 992):
-                for u in (4, 8):
+            for tr in (64, 128, 256, 512, 992):
+                for u in (1, 2, 4, 8):
                     a = mkargs(pattern=1, reduce_threads=tr)
                     timed(dict(kind="mix", how="tma_ring", grid=grid, reduce_threads=tr, copy_threads=1, unroll=u),
                           lambda: probe.fxp_mix_tma(grid, tr + 32, u, C.byref(a), sptr))
@@ -208,7 +210,8 @@ def main():
         dist.barrier()
         bar = {}
         epochs = {0: 0, 1: 0, 2: 0}
-        for variant in ((0, 1, 2) if have_mc else (0, 2)):
+        epochs[3] = 0
+        for variant in ((0, 1, 2, 3) if have_mc else (0, 2, 3)):
             vals = []
             for rep in range(3):
                 a = mkargs(iters=200, epoch0=epochs[variant])
@@ -232,16 +235,17 @@ def main():
             row["copy_gbs_rw"] = 2 * (2 * nbytes) / (ms * 1e-3) / 1e9
         emit(**row)
     if lat is not None:
-        lt = torch.tensor(lat[:7], dtype=torch.float64)
+        lt = torch.tensor(lat[:10], dtype=torch.float64)
         dist.all_reduce(lt, op=dist.ReduceOp.MAX)
         names = ["local_ld_ns", "peer_ld_ns", "multimem_ld_reduce_ns", "multimem_st_fence_ns", "peer_st_fence_ns",
-                 "local_st_fence_ns", "fence_ns"]
+                 "local_st_fence_ns", "fence_ns", "fence_gpu_ns", "local_st_fence_gpu_ns", "multimem_st_fence_gpu_ns"]
         emit(kind="latency", **{n: v for n, v in zip(names, lt.tolist())})
         for variant, vals in bar.items():
             bt = torch.tensor(vals, dtype=torch.float64)
             dist.all_reduce(bt, op=dist.ReduceOp.MAX)
             emit(kind="barrier", variant={0: "W x st.release.sys + ld.acquire.sys", 1: "one multimem.red.release + ld.acquire.sys",
-                                          2: "fence + W x st.relaxed.sys, relaxed poll + fence"}[variant],
+                                          2: "fence + W x st.relaxed.sys, relaxed poll + fence",
+                                          3: "gpu-scope fence + W x st.relaxed.sys, relaxed poll + gpu-scope fence"}[variant],
                  ns_per_barrier=bt.tolist())
     torch.cuda.synchronize()
     if world > 1:

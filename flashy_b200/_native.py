@@ -23,6 +23,8 @@ FX_COMM_MEM_AUTO, FX_COMM_MEM_VMM, FX_COMM_MEM_IPC, FX_COMM_HOST_ONLY = 0, 1, 2,
 FX_MAX_WORLD = 16
 
 ALGO_NAMES = {FX_ALGO_ONE_SHOT: "one_shot", FX_ALGO_TWO_SHOT: "two_shot", FX_ALGO_NVLS: "nvls"}
+KERNEL_NAMES = {1: "k_one_shot", 2: "k_two_shot", 3: "k_nvls", 4: "k_pipe<NVLS=false>", 5: "k_pipe<NVLS=true>",
+                6: "k_fuse<NVLS=false>", 7: "k_fuse<NVLS=true>"}
 
 # Every symbol include/flashy_b200.h declares (tests check the .so exports all of them).
 EXPORTS = (
@@ -50,6 +52,7 @@ class PlanInfo(C.Structure):
         ("algo", C.c_int), ("grid_x", C.c_int), ("block", C.c_int),
         ("total_elems", C.c_uint64), ("padded_elems", C.c_uint64), ("shard_elems", C.c_uint64),
         ("wire_bytes", C.c_uint64), ("region_offset", C.c_uint64 * 2), ("signature", C.c_uint64),
+        ("kernel", C.c_int), ("chunks", C.c_int), ("chunk_bytes", C.c_uint64),
     ]
 
 

@@ -1,0 +1,370 @@
+// k_fuse: the bucketed all-reduce as ONE kernel of five decoupled warp roles per CTA, with the
+// bucket <-> tensor traffic staged through shared memory by the TMA engine (cp.async.bulk).
+//
+// Replaces, for float buckets averaged / summed in their own dtype, the per-tensor loop
+//     all_reduce(t.data, SUM, async_op=True) ... handle.wait(); t.data /= world_size()
+// of the reference (flashy/distrib.py:105-111) by a single launch.
+//
+// Layout (as in fx_kernels.cu): the bucket is W shards x gridDim.x slices; CTA b owns slice b of
+// every shard and cuts it into `chunks` chunks of `chunk_elems` elements.  Chunk c of CTA b is
+// W sub-ranges (one per shard) of <= FZ chunk bytes each.  Roles of a CTA:
+//
+//   pack    (1 warp)  tensors -> shared memory (cp.async.bulk, mbarrier) -> own arena, chunk by
+//                     chunk, then "chunk c packed" to every peer's flags_pack[b][me]
+//   poll    (1 warp)  reads flags_pack[b][*] / flags_red[b][*] of the own pad and publishes the
+//                     minimum over ranks in shared memory (what every rank has packed / reduced)
+//   reduce  (12 warps) one warp per chunk, chunks round-robin: multimem.ld_reduce of the own
+//                     shard's sub-range through the NVSwitch, / W, multimem.st to all arenas
+//                     (or, without multicast: pull the W arenas in rank order, write the own one)
+//   signal  (1 warp)  watches the reduce warps' progress in shared memory, fences ONCE at system
+//                     scope and writes "chunks < n of shard me are reduced" to every peer
+//   unpack  (1 warp)  arena (own after NVLS, peers' otherwise) -> shared memory -> output tensors
+//
+// The reduce warps therefore never execute a system-scope fence (1.75 us each on this system,
+// profiles/r02_nvls_probe_*.jsonl) and never wait for their own stores: the NVLink stream of a
+// CTA only stalls when a peer is late.  Pieces whose tensor address is not 16-byte aligned and
+// the (< 16 byte) tails of odd-sized tensors go through ordinary loads / stores of the same warp.
+#include "fx_device.cuh"
+
+namespace {
+
+#define FZ_THREADS 512
+#define FZ_WARP_POLL 0
+#define FZ_WARP_SIG 1
+#define FZ_WARP_PACK 2
+#define FZ_WARP_UNPACK 3
+#define FZ_WARP_RED0 4
+#define FZ_RED_WARPS 12
+
+// ---------------------------------------------------------------------------- shared-memory sync
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void st_release_cta(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" :: "r"(smem_u32(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_cta(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------- TMA (cp.async.bulk)
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load(void* smem, const void* gptr, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(smem)), "l"(gptr), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_store(void* gptr, const void* smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(gptr), "r"(smem_u32(smem)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// generic-proxy writes to shared memory -> visible to the async proxy (a following bulk store)
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+struct FuseSync {
+    uint64_t full_pack[2], full_unp[2];    // "the bulk loads of this half have landed"
+    uint32_t packed;                       // chunks every rank has packed (this launch)
+    uint32_t reduced;                      // chunks of every shard reduced and delivered
+    uint32_t red_prog[FZ_RED_WARPS];       // chunks completed by each reduce warp
+    uint32_t abort;                        // a peer never arrived: stop without touching the outputs
+};
+
+// Spin until *counter >= want (shared memory); false if the launch was aborted.
+__device__ __forceinline__ bool wait_count(const uint32_t* counter, uint32_t want, const uint32_t* abort) {
+    while (ld_acquire_cta(counter) < want) {
+        if (*reinterpret_cast<const volatile uint32_t*>(abort)) return false;
+        __nanosleep(20);
+    }
+    return true;
+}
+
+// The pieces of bucket range [lo, hi) (elements): for each tensor i intersecting it calls
+// f(i, p0, p1) with the intersection [p0, p1).
+template <typename F>
+__device__ __forceinline__ void for_pieces(const Meta& m, long long lo, long long hi, F f) {
+    if (lo >= m.off[m.n]) return;
+    for (int i = find_tensor(m.off, m.n, lo); i < m.n && m.off[i] < hi; ++i) {
+        const long long t0 = m.off[i], t1 = t0 + m.numel[i];
+        const long long p0 = lo > t0 ? lo : t0, p1 = hi < t1 ? hi : t1;
+        if (p1 > p0) f(i, p0, p1);
+    }
+}
+
+template <typename T, bool NVLS, int W>
+__global__ void __launch_bounds__(FZ_THREADS, 1) k_fuse(const FxLaunch a) {
+    extern __shared__ __align__(128) unsigned char fz_dyn[];
+    __shared__ MetaSmem meta_smem;
+    __shared__ FuseSync sy;
+
+    const int l = blockIdx.y, b = blockIdx.x;
+    const int rank = a.rank0 + l;
+    const int world = W > 0 ? W : a.world;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    FxPlanState* st = a.state + l;
+    char* my = a.arena[rank];
+    // the two owner-private words this launch depends on, fetched together
+    const uint32_t calls = ld_volatile_u32(&st->calls);
+    const uint32_t base = ld_volatile_u32(&pad_of(my)->pipe_epoch[b]);
+    const Meta m = load_meta(a, l, &meta_smem);                 // (contains a __syncthreads)
+    if (threadIdx.x == 0) {
+        mbar_init(&sy.full_pack[0], 1); mbar_init(&sy.full_pack[1], 1);
+        mbar_init(&sy.full_unp[0], 1); mbar_init(&sy.full_unp[1], 1);
+        sy.packed = 0; sy.reduced = 0; sy.abort = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (threadIdx.x < FZ_RED_WARPS) sy.red_prog[threadIdx.x] = 0;
+    __syncthreads();
+
+    const unsigned long long region = a.region[calls & 1];
+    const long long slice = a.slice_elems, shard = a.shard_elems, csz = a.chunk_elems;
+    const int chunks = a.chunks;
+    const bool avg = a.op == FX_AVG;
+    constexpr long long VEC = FX_VEC_BYTES / (long long)sizeof(T);
+    const uint32_t cb = (uint32_t)(csz * sizeof(T));            // bytes of one full sub-range chunk
+    unsigned char* pack_buf = fz_dyn;                           // [2][world * cb]
+    unsigned char* unp_buf = fz_dyn + 2ull * world * cb;        // [2][world * cb]
+
+    if (warp == FZ_WARP_POLL) {
+        // ------------------------------------------------------------ poll: peers' progress -> smem
+        const int which = lane >> 4, q = lane & 15;
+        const bool active = q < world;
+        const uint32_t* flag = pipe_flag(my, which, b, active ? q : 0);
+        uint32_t published = 0;
+        unsigned long long t0 = 0;
+        uint32_t spins = 0;
+        while (true) {
+            uint32_t v = (uint32_t)chunks;
+            if (active) {
+                const int32_t d = (int32_t)(ld_acquire_sys(flag) - base);
+                v = d < 0 ? 0u : ((uint32_t)d > (uint32_t)chunks ? (uint32_t)chunks : (uint32_t)d);
+            }
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) { const uint32_t w = __shfl_xor_sync(0xffffffffu, v, o); v = w < v ? w : v; }
+            if (q == 0 && v > published) {
+                st_release_cta(which == FX_FLAG_PACK ? &sy.packed : &sy.reduced, v);
+                published = v;
+            }
+            if (__all_sync(0xffffffffu, v >= (uint32_t)chunks)) break;
+            if ((++spins & 0xff) == 0) {
+                const unsigned long long now = globaltimer_ns();
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > a.timeout_ns) {               // a peer never arrived
+                    if (lane == 0) {
+                        *reinterpret_cast<volatile uint32_t*>(a.status) = (uint32_t)(-FX_ERR_TIMEOUT);
+                        __threadfence_system();
+                        *reinterpret_cast<volatile uint32_t*>(&sy.abort) = 1;
+                    }
+                    break;
+                }
+            }
+        }
+    } else if (warp == FZ_WARP_SIG) {
+        // ------------------------------------------------------------ signal: reduced chunks -> peers
+        int next = 0;
+        while (next < chunks) {
+            const int c = next + lane;
+            bool done = false;
+            if (c < chunks) done = ld_acquire_cta(&sy.red_prog[c % FZ_RED_WARPS]) > (uint32_t)(c / FZ_RED_WARPS);
+            const unsigned mask = __ballot_sync(0xffffffffu, done);
+            const int n = __ffs(~mask) - 1;                        // leading chunks that are complete (32 if all)
+            const int adv = n < 0 ? 32 : n;
+            if (adv == 0) {
+                if (*reinterpret_cast<const volatile uint32_t*>(&sy.abort)) break;
+                __nanosleep(40);
+                continue;
+            }
+            next += adv;
+            fence_sys();                                           // the reduce warps' stores, cumulatively
+            if (lane < world) st_relaxed_sys(pipe_flag(a.arena[lane], FX_FLAG_RED, b, rank), base + (uint32_t)next);
+        }
+    } else if (warp == FZ_WARP_PACK) {
+        // ------------------------------------------------------------ pack: tensors -> smem -> arena
+        for (int c = 0; c < chunks; ++c) {
+            const long long c0 = c * csz, c1 = (c0 + csz < slice) ? c0 + csz : slice;
+            const int half = c & 1;
+            unsigned char* buf = pack_buf + (size_t)half * world * cb;
+            if (c >= 2) { if (lane == 0) tma_wait_read1(); __syncwarp(); }      // the stores of chunk c-2 left this half
+            uint32_t tx = 0;
+            bool generic = false;
+            for (int s = 0; s < world; ++s) {
+                const long long lo = s * shard + b * slice + c0, hi = lo + (c1 - c0);
+                unsigned char* sbase = buf + (size_t)s * cb;
+                for_pieces(m, lo, hi, [&](int i, long long p0, long long p1) {
+                    const T* src = static_cast<const T*>(m.in[i]) + (p0 - m.off[i]);
+                    T* dst = reinterpret_cast<T*>(sbase) + (p0 - lo);
+                    const long long n = p1 - p0;
+                    long long bulk = 0;
+                    if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+                        bulk = n / VEC * VEC;
+                        if (bulk) {
+                            if (lane == 0) tma_load(dst, src, (uint32_t)(bulk * sizeof(T)), &sy.full_pack[half]);
+                            tx += (uint32_t)(bulk * sizeof(T));
+                        }
+                    }
+                    if (bulk < n) {
+                        for (long long e = bulk + lane; e < n; e += 32) dst[e] = src[e];
+                        generic = true;
+                    }
+                });
+            }
+            if (generic) fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_expect_tx(&sy.full_pack[half], tx);
+            if (c >= 1) {                                          // chunk c-1 is in the arena: tell everybody
+                if (lane == 0) tma_wait_all();
+                __syncwarp();
+                if (lane < world) st_release_sys(pipe_flag(a.arena[lane], FX_FLAG_PACK, b, rank), base + (uint32_t)c);
+            }
+            mbar_wait(&sy.full_pack[half], (uint32_t)((c >> 1) & 1));
+            if (lane == 0) {
+                for (int s = 0; s < world; ++s) {
+                    const long long lo = s * shard + b * slice + c0;
+                    tma_store(my + region + (unsigned long long)lo * sizeof(T), buf + (size_t)s * cb, (uint32_t)((c1 - c0) * sizeof(T)));
+                }
+                tma_commit();
+            }
+        }
+        if (lane == 0) tma_wait_all();
+        __syncwarp();
+        if (lane < world) st_release_sys(pipe_flag(a.arena[lane], FX_FLAG_PACK, b, rank), base + (uint32_t)chunks);
+    } else if (warp == FZ_WARP_UNPACK) {
+        // ------------------------------------------------------------ unpack: arena -> smem -> tensors
+        for (int c = 0; c < chunks; ++c) {
+            if (!wait_count(&sy.reduced, (uint32_t)c + 1, &sy.abort)) break;
+            const long long c0 = c * csz, c1 = (c0 + csz < slice) ? c0 + csz : slice;
+            const uint32_t bytes = (uint32_t)((c1 - c0) * sizeof(T));
+            const int half = c & 1;
+            unsigned char* buf = unp_buf + (size_t)half * world * cb;
+            if (lane == 0) {
+                if (c >= 2) tma_wait_read1();                      // the stores of chunk c-2 left this half
+                mbar_expect_tx(&sy.full_unp[half], bytes * (uint32_t)world);
+                for (int s = 0; s < world; ++s) {
+                    const long long lo = s * shard + b * slice + c0;
+                    const char* from = (NVLS ? my : a.arena[s]) + region + (unsigned long long)lo * sizeof(T);
+                    tma_load(buf + (size_t)s * cb, from, bytes, &sy.full_unp[half]);
+                }
+            }
+            mbar_wait(&sy.full_unp[half], (uint32_t)((c >> 1) & 1));
+            for (int s = 0; s < world; ++s) {
+                const long long lo = s * shard + b * slice + c0, hi = lo + (c1 - c0);
+                const unsigned char* sbase = buf + (size_t)s * cb;
+                for_pieces(m, lo, hi, [&](int i, long long p0, long long p1) {
+                    T* dst = static_cast<T*>(m.out[i]) + (p0 - m.off[i]);
+                    const T* src = reinterpret_cast<const T*>(sbase) + (p0 - lo);
+                    const long long n = p1 - p0;
+                    long long bulk = 0;
+                    if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+                        bulk = n / VEC * VEC;
+                        if (bulk && lane == 0) tma_store(dst, src, (uint32_t)(bulk * sizeof(T)));
+                    }
+                    for (long long e = bulk + lane; e < n; e += 32) dst[e] = src[e];
+                });
+            }
+            if (lane == 0) tma_commit();
+            __syncwarp();
+        }
+        if (lane == 0) tma_wait_all();
+    } else {
+        // ------------------------------------------------------------ reduce: one warp per chunk
+        const int rw = warp - FZ_WARP_RED0;
+        uint32_t mine = 0;
+        for (int c = rw; c < chunks; c += FZ_RED_WARPS) {
+            if (!wait_count(&sy.packed, (uint32_t)c + 1, &sy.abort)) break;
+            const long long c0 = c * csz, c1 = (c0 + csz < slice) ? c0 + csz : slice;
+            const long long nvec = (c1 - c0) / VEC;
+            const unsigned long long byte_off = region + (unsigned long long)(rank * shard + b * slice + c0) * sizeof(T);
+            if (NVLS) {
+                char* mc = a.mc_arena + byte_off;
+                constexpr int U = 8;
+                for (long long v0 = lane; v0 < nvec; v0 += 32 * U) {
+                    uint4 r[U];
+#pragma unroll
+                    for (int k = 0; k < U; ++k) { const long long v = v0 + 32 * k; if (v < nvec) r[k] = Multimem<T>::ld_reduce(mc + v * FX_VEC_BYTES); }
+#pragma unroll
+                    for (int k = 0; k < U; ++k) { const long long v = v0 + 32 * k; if (v < nvec) multimem_st(mc + v * FX_VEC_BYTES, avg ? scale_vec<T>(r[k], world) : r[k]); }
+                }
+            } else {
+                reduce_vectors<T, W, FX_SUM>(a, world, byte_off, nvec, avg, my, Lane{lane, 32});
+            }
+            __syncwarp();
+            if (lane == 0) st_release_cta(&sy.red_prog[rw], ++mine);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        pad_of(my)->pipe_epoch[b] = base + (uint32_t)chunks;
+        if (atomicAdd(&st->finished, 1u) == gridDim.x - 1) {
+            st->finished = 0;
+            *reinterpret_cast<volatile uint32_t*>(&st->calls) = calls + 1;
+        }
+    }
+}
+
+template <typename K>
+int launch_fuse(K kernel, const fx_plan* plan, const FxLaunch& args, size_t smem, cudaStream_t stream) {
+    static thread_local const void* configured[32];
+    static thread_local int n_configured = 0;
+    const void* fn = reinterpret_cast<const void*>(kernel);
+    bool seen = false;
+    for (int i = 0; i < n_configured; ++i) seen = seen || configured[i] == fn;
+    if (!seen) {
+        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 << 10);
+        if (e != cudaSuccess) return fx_fail(FX_ERR_CUDA, "cudaFuncSetAttribute(k_fuse): %s", cudaGetErrorString(e));
+        if (n_configured < 32) configured[n_configured++] = fn;
+    }
+    dim3 grid(plan->grid_x, args.n_local), block(FZ_THREADS);
+    void* params[] = {const_cast<FxLaunch*>(&args)};
+    cudaError_t e = args.n_local > 1
+        ? cudaLaunchCooperativeKernel(fn, grid, block, params, smem, stream)      // virtual ranks must be co-resident
+        : cudaLaunchKernel(fn, grid, block, params, smem, stream);
+    if (e != cudaSuccess) return fx_fail(FX_ERR_CUDA, "k_fuse launch failed: %s", cudaGetErrorString(e));
+    return FX_OK;
+}
+
+template <typename T>
+int launch_fuse_t(fx_plan* plan, const FxLaunch& a, size_t smem, cudaStream_t s) {
+    if (plan->algo == FX_ALGO_NVLS) return launch_fuse(k_fuse<T, true, 0>, plan, a, smem, s);
+    switch (a.world) {
+        case 2: return launch_fuse(k_fuse<T, false, 2>, plan, a, smem, s);
+        case 4: return launch_fuse(k_fuse<T, false, 4>, plan, a, smem, s);
+        case 8: return launch_fuse(k_fuse<T, false, 8>, plan, a, smem, s);
+    }
+    return launch_fuse(k_fuse<T, false, 0>, plan, a, smem, s);
+}
+
+}  // namespace
+
+size_t fx_fuse_smem_bytes(int world, long long chunk_bytes) { return 4ull * world * chunk_bytes; }
+
+int fx_launch_fuse(fx_plan* plan, const FxLaunch& a, cudaStream_t s) {
+    if (plan->algo == FX_ALGO_NVLS && !a.mc_arena) return fx_fail(FX_ERR_STATE, "NVLS plan without a multicast mapping");
+    const size_t smem = fx_fuse_smem_bytes(a.world, a.chunk_elems * (long long)plan->wsize);
+    switch (plan->wire) {
+        case FX_F32: return launch_fuse_t<float>(plan, a, smem, s);
+        case FX_BF16: return launch_fuse_t<__nv_bfloat16>(plan, a, smem, s);
+        case FX_F16: return launch_fuse_t<__half>(plan, a, smem, s);
+    }
+    return fx_fail(FX_ERR_UNSUPPORTED, "the fused kernel handles fp32 / bf16 / fp16 buckets only");
+}

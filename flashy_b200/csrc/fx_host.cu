@@ -866,6 +866,21 @@ extern "C" int fx_plan_create(fx_comm* c, int world, const int64_t* numels, int 
         p->chunks = (int)((p->slice + p->chunk - 1) / p->chunk);
     }
 
+    // Fused five-role kernel with TMA staging (fx_fuse.cu): float buckets reduced in their own dtype.
+    // FLASHY_B200_FUSE: 0 never, 1 (default) whenever eligible.  One chunk = one reduce warp's batch.
+    const bool fuse_able = algo != FX_ALGO_ONE_SHOT && dtype == wire_dtype &&
+                           (wire_dtype == FX_F32 || wire_dtype == FX_BF16 || wire_dtype == FX_F16);
+    if (fuse_able && env_ll("FLASHY_B200_FUSE", 1) != 0) {
+        long long cbytes = env_ll("FLASHY_B200_FUSE_CHUNK", 4096);
+        cbytes = std::max<long long>(FX_SLICE_ALIGN, cbytes / FX_SLICE_ALIGN * FX_SLICE_ALIGN);
+        while (cbytes > FX_SLICE_ALIGN && fx_fuse_smem_bytes(world, cbytes) > (size_t)(160 << 10)) cbytes /= 2;
+        cbytes = cbytes / FX_SLICE_ALIGN * FX_SLICE_ALIGN;
+        if (fx_fuse_smem_bytes(world, cbytes) <= (size_t)(160 << 10)) {
+            p->fuse_chunk = cbytes / (long long)wsize;
+            p->fuse_chunks = (int)((p->slice + p->fuse_chunk - 1) / p->fuse_chunk);
+        }
+    }
+
     if (c && !c->host_only) {
         std::lock_guard<std::mutex> lock(c->mu);
         const size_t need = round_up(p->wire_bytes, 256);
@@ -928,6 +943,12 @@ extern "C" int fx_plan_get_info(fx_plan* p, fx_plan_info* info) {
     info->wire_bytes = p->wire_bytes;
     info->region_offset[0] = p->region[0]; info->region_offset[1] = p->region[1];
     info->signature = p->signature;
+    info->kernel = fx_plan_kernel_id(p, FX_SUM);
+    if (info->kernel == FX_KERNEL_FUSE_P2P || info->kernel == FX_KERNEL_FUSE_NVLS) {
+        info->chunks = p->fuse_chunks; info->chunk_bytes = (uint64_t)p->fuse_chunk * p->wsize;
+    } else if (info->kernel == FX_KERNEL_PIPE_P2P || info->kernel == FX_KERNEL_PIPE_NVLS) {
+        info->chunks = p->chunks; info->chunk_bytes = (uint64_t)p->chunk * p->wsize;
+    }
     return FX_OK;
 }
 
@@ -1071,9 +1092,25 @@ extern "C" int fx_allreduce(fx_plan* p, int op, const void* const* in_ptrs, void
     FxLaunch a;
     fill_launch(c, p, a);
     a.op = op; a.mode = FX_MODE_FUSED;
-    rc = fx_launch_allreduce(p, a, s);
+    const int kid = fx_plan_kernel_id(p, op);
+    if (kid == FX_KERNEL_FUSE_P2P || kid == FX_KERNEL_FUSE_NVLS) {
+        a.chunks = p->fuse_chunks; a.chunk_elems = p->fuse_chunk;
+        rc = fx_launch_fuse(p, a, s);
+    } else {
+        rc = fx_launch_allreduce(p, a, s);
+    }
     if (rc == FX_OK) c->launches++;
     return rc;
+}
+
+int fx_plan_kernel_id(const fx_plan* p, int op) {
+    const bool sum = op == FX_SUM || op == FX_AVG;
+    if (p->algo == FX_ALGO_ONE_SHOT) return FX_KERNEL_ONE_SHOT;
+    const bool nvls = p->algo == FX_ALGO_NVLS && sum;
+    if (sum && p->fuse_chunks > 0) return nvls ? FX_KERNEL_FUSE_NVLS : FX_KERNEL_FUSE_P2P;
+    const bool pipe_ok = p->wire == FX_F32 || p->wire == FX_BF16 || p->wire == FX_F16;
+    if (sum && p->chunks > 0 && pipe_ok) return nvls ? FX_KERNEL_PIPE_NVLS : FX_KERNEL_PIPE_P2P;
+    return nvls ? FX_KERNEL_NVLS : FX_KERNEL_TWO_SHOT;
 }
 
 extern "C" int fx_allreduce_begin(fx_plan* p, int op, const void* const* in_ptrs, void* stream) {

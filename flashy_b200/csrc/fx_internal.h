@@ -136,6 +136,8 @@ struct fx_plan {
     long long total = 0, padded = 0, shard = 0, slice = 0;
     int chunks = 0;                             // pipelined kernel: chunks per slice (0 = classic kernels)
     long long chunk = 0;
+    int fuse_chunks = 0;                        // fused TMA kernel (fx_fuse.cu): chunks per slice (0 = not eligible)
+    long long fuse_chunk = 0;                   // elements per chunk of one sub-range
     size_t esize = 0, wsize = 0, wire_bytes = 0;
     size_t region[2] = {0, 0};
     bool recycled = false;                      // region memory was used by an earlier plan
@@ -168,6 +170,11 @@ int fx_launch_allreduce(fx_plan* plan, const FxLaunch& args, cudaStream_t stream
 int fx_launch_broadcast(fx_plan* plan, const FxLaunch& args, cudaStream_t stream);
 int fx_launch_unpack(fx_plan* plan, const FxLaunch& args, cudaStream_t stream);
 int fx_launch_barrier(fx_comm* comm, const FxLaunch& args, cudaStream_t stream);
+// Fused five-role kernel with TMA staging (fx_fuse.cu): float SUM / AVG buckets sent in their own dtype.
+int fx_launch_fuse(fx_plan* plan, const FxLaunch& args, cudaStream_t stream);
+size_t fx_fuse_smem_bytes(int world, long long chunk_bytes);
+// fx_kernel_id of the kernel an all-reduce of `op` on this plan launches (FUSED mode).
+int fx_plan_kernel_id(const fx_plan* plan, int op);
 // Largest gridDim.x such that gridDim.x * n_local CTAs of the widest kernel are co-resident.
 int fx_max_coresident_blocks(int device, int n_local, int* sm_count);
 bool fx_kernel_supported(int dtype, int wire, int op, bool broadcast);

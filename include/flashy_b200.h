@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define FX_ABI_VERSION 1
+#define FX_ABI_VERSION 2
 #define FX_MAX_WORLD 16          /* single NVSwitch domain; >8 only reachable with virtual ranks */
 #define FX_MAX_BLOCKS 512        /* upper bound of gridDim.x for any collective kernel */
 
@@ -67,6 +67,17 @@ typedef enum fx_algo {
     FX_ALGO_NVLS = 3             /* multimem.ld_reduce / multimem.st through the NVSwitch (needs multicast) */
 } fx_algo;
 
+/* Which kernel a SUM / AVG all-reduce of a plan launches (fx_plan_info.kernel). */
+typedef enum fx_kernel_id {
+    FX_KERNEL_ONE_SHOT = 1,      /* k_one_shot  */
+    FX_KERNEL_TWO_SHOT = 2,      /* k_two_shot  (three barrier-separated phases, register copies) */
+    FX_KERNEL_NVLS = 3,          /* k_nvls      (same, multimem reduce phase) */
+    FX_KERNEL_PIPE_P2P = 4,      /* k_pipe<.., NVLS=false>  (warp roles, register copies) */
+    FX_KERNEL_PIPE_NVLS = 5,     /* k_pipe<.., NVLS=true> */
+    FX_KERNEL_FUSE_P2P = 6,      /* k_fuse<.., NVLS=false>  (five decoupled roles, cp.async.bulk staging) */
+    FX_KERNEL_FUSE_NVLS = 7      /* k_fuse<.., NVLS=true> */
+} fx_kernel_id;
+
 /* fx_comm_create flags */
 #define FX_COMM_MEM_AUTO   0u    /* VMM (cuMemCreate, fd export) if the driver allows, else cudaMalloc + cudaIpc */
 #define FX_COMM_MEM_VMM    1u
@@ -97,6 +108,9 @@ typedef struct fx_plan_info {
     uint64_t wire_bytes;         /* padded_elems * sizeof(wire dtype) = one staging copy */
     uint64_t region_offset[2];   /* the two (double-buffered) staging regions inside each arena */
     uint64_t signature;          /* hash of (n, dtype, numels): what ranks must agree on */
+    int kernel;                  /* fx_kernel_id a SUM / AVG fx_allreduce of this plan launches */
+    int chunks;                  /* chunks per slice of that kernel (0: not chunked) */
+    uint64_t chunk_bytes;        /* bytes of one chunk of one shard's slice */
 } fx_plan_info;
 
 /* ------------------------------------------------------------------ errors / build info */
