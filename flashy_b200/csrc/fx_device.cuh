@@ -127,8 +127,8 @@ __device__ __forceinline__ Meta load_meta(const FxLaunch& a, int l, MetaSmem* sm
     const void* const* g_in = a.in_ptrs + (long long)l * a.n;
     void* const* g_out = a.out_ptrs + (long long)l * a.n;
     if (a.n <= FX_SMEM_TENSORS) {
-        for (int i = threadIdx.x; i <= a.n; i += FX_THREADS) sm->off[i] = g_off[i];
-        for (int i = threadIdx.x; i < a.n; i += FX_THREADS) {
+        for (int i = threadIdx.x; i <= a.n; i += (int)blockDim.x) sm->off[i] = g_off[i];
+        for (int i = threadIdx.x; i < a.n; i += (int)blockDim.x) {
             sm->numel[i] = g_numel[i];
             sm->in[i] = g_in[i];
             sm->out[i] = g_out[i];

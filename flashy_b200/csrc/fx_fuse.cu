@@ -13,28 +13,30 @@
 //                     chunk, then "chunk c packed" to every peer's flags_pack[b][me]
 //   poll    (1 warp)  reads flags_pack[b][*] / flags_red[b][*] of the own pad and publishes the
 //                     minimum over ranks in shared memory (what every rank has packed / reduced)
-//   reduce  (12 warps) one warp per chunk, chunks round-robin: multimem.ld_reduce of the own
+//   reduce  (4 warps) one warp per chunk, chunks round-robin: multimem.ld_reduce of the own
 //                     shard's sub-range through the NVSwitch, / W, multimem.st to all arenas
 //                     (or, without multicast: pull the W arenas in rank order, write the own one)
 //   signal  (1 warp)  watches the reduce warps' progress in shared memory, fences ONCE at system
 //                     scope and writes "chunks < n of shard me are reduced" to every peer
 //   unpack  (1 warp)  arena (own after NVLS, peers' otherwise) -> shared memory -> output tensors
 //
-// The reduce warps therefore never execute a system-scope fence (1.75 us each on this system,
-// profiles/r02_nvls_probe_*.jsonl) and never wait for their own stores: the NVLink stream of a
+// Four reduce warps x 8 vectors per lane keep ~1 K multimem requests in flight per SM: the
+// measured optimum next to the copy traffic (more than ~2 K per SM slows BOTH down: 840 -> 560 GB/s
+// bus in benchmarks/nvls_probe.py).  The reduce warps never execute a system-scope fence (1.75 us each on this system,
+// profiles/r02_nvls_probe_n8.jsonl) and never wait for their own stores: the NVLink stream of a
 // CTA only stalls when a peer is late.  Pieces whose tensor address is not 16-byte aligned and
 // the (< 16 byte) tails of odd-sized tensors go through ordinary loads / stores of the same warp.
 #include "fx_device.cuh"
 
 namespace {
 
-#define FZ_THREADS 512
+#define FZ_THREADS 256
 #define FZ_WARP_POLL 0
 #define FZ_WARP_SIG 1
 #define FZ_WARP_PACK 2
 #define FZ_WARP_UNPACK 3
 #define FZ_WARP_RED0 4
-#define FZ_RED_WARPS 12
+#define FZ_RED_WARPS 4
 
 // ---------------------------------------------------------------------------- shared-memory sync
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -50,6 +52,16 @@ __device__ __forceinline__ void st_relaxed_sys(uint32_t* p, uint32_t v) {
     asm volatile("st.relaxed.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void fence_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+__device__ __forceinline__ void fence_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+
+// "chunks < n of my copy are packed": the packed data sits in THIS GPU's memory (written by bulk
+// stores that have completed), and every reader -- the switch for multimem.ld_reduce, a peer's
+// plain load -- is served by this GPU's L2, so ordering the flag behind the data at GPU scope is
+// enough; a system-scope fence costs 1.76 us here against 0.14 us (benchmarks/nvls_probe.py).
+__device__ __forceinline__ void signal_packed(const FxLaunch& a, int lane, int world, int rank, int b, uint32_t value) {
+    fence_gpu();
+    if (lane < world) st_relaxed_sys(pipe_flag(a.arena[lane], FX_FLAG_PACK, b, rank), value);
+}
 
 // ---------------------------------------------------------------------------- TMA (cp.async.bulk)
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
@@ -235,7 +247,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_fuse(const FxLaunch a) {
             if (c >= 1) {                                          // chunk c-1 is in the arena: tell everybody
                 if (lane == 0) tma_wait_all();
                 __syncwarp();
-                if (lane < world) st_release_sys(pipe_flag(a.arena[lane], FX_FLAG_PACK, b, rank), base + (uint32_t)c);
+                signal_packed(a, lane, world, rank, b, base + (uint32_t)c);
             }
             mbar_wait(&sy.full_pack[half], (uint32_t)((c >> 1) & 1));
             if (lane == 0) {
@@ -248,7 +260,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_fuse(const FxLaunch a) {
         }
         if (lane == 0) tma_wait_all();
         __syncwarp();
-        if (lane < world) st_release_sys(pipe_flag(a.arena[lane], FX_FLAG_PACK, b, rank), base + (uint32_t)chunks);
+        signal_packed(a, lane, world, rank, b, base + (uint32_t)chunks);
     } else if (warp == FZ_WARP_UNPACK) {
         // ------------------------------------------------------------ unpack: arena -> smem -> tensors
         for (int c = 0; c < chunks; ++c) {
