@@ -342,7 +342,7 @@ int launch_fuse(K kernel, const fx_plan* plan, const FxLaunch& args, size_t smem
     bool seen = false;
     for (int i = 0; i < n_configured; ++i) seen = seen || configured[i] == fn;
     if (!seen) {
-        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 << 10);
+        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 << 10);
         if (e != cudaSuccess) return fx_fail(FX_ERR_CUDA, "cudaFuncSetAttribute(k_fuse): %s", cudaGetErrorString(e));
         if (n_configured < 32) configured[n_configured++] = fn;
     }
