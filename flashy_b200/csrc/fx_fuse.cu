@@ -90,13 +90,32 @@ __device__ __forceinline__ void tma_store(void* gptr, const void* smem, uint32_t
                  :: "l"(gptr), "r"(smem_u32(smem)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void tma_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
-__device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// Wait until at most `n` of this thread's bulk groups are still reading shared memory / still in flight.
+__device__ __forceinline__ void tma_wait_read(int n) {
+    if (n <= 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    else if (n == 1) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+    else asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+}
+__device__ __forceinline__ void tma_wait_done(int n) {
+    if (n <= 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    else asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");
+}
 // generic-proxy writes to shared memory -> visible to the async proxy (a following bulk store)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// Debug trace of CTA 0 (FLASHY_B200_TRACE=1): globaltimer stamps, FZ_TR_CHUNKS chunks at most.
+#define FZ_TR_CHUNKS 1024
+#define FZ_TR_PACK 16                                  // [c][4]: loads issued, loads landed, stores complete(d), signalled
+#define FZ_TR_UNPACK (FZ_TR_PACK + 4 * FZ_TR_CHUNKS)   // [c][4]: reduced seen, loads issued, loads landed, stores issued
+#define FZ_TR_RED (FZ_TR_UNPACK + 4 * FZ_TR_CHUNKS)    // [c][4]: start wait, packed seen, stores issued, -
+#define FZ_TR_SIG (FZ_TR_RED + 4 * FZ_TR_CHUNKS)       // [c][2]: detected, fence done
+#define FZ_TR_POLLP (FZ_TR_SIG + 2 * FZ_TR_CHUNKS)     // [c]: "c+1 chunks packed everywhere" published
+#define FZ_TR_POLLR (FZ_TR_POLLP + FZ_TR_CHUNKS)       // [c]: "c+1 chunks reduced everywhere" published
+#define FZ_TR_WORDS (FZ_TR_POLLR + FZ_TR_CHUNKS)
+
+#define FZ_NB 3                             // staging buffers per copy role (chunks in flight)
 struct FuseSync {
-    uint64_t full_pack[2], full_unp[2];    // "the bulk loads of this half have landed"
+    uint64_t full_pack[FZ_NB], full_unp[FZ_NB];   // "the bulk loads of this buffer have landed"
     uint32_t packed;                       // chunks every rank has packed (this launch)
     uint32_t reduced;                      // chunks of every shard reduced and delivered
     uint32_t red_prog[FZ_RED_WARPS];       // chunks completed by each reduce warp
@@ -139,10 +158,11 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_fuse(const FxLaunch a) {
     // the two owner-private words this launch depends on, fetched together
     const uint32_t calls = ld_volatile_u32(&st->calls);
     const uint32_t base = ld_volatile_u32(&pad_of(my)->pipe_epoch[b]);
+    const unsigned long long t_enter = (a.trace && b == 0 && l == 0 && threadIdx.x == 0) ? globaltimer_ns() : 0;
     const Meta m = load_meta(a, l, &meta_smem);                 // (contains a __syncthreads)
+    if (a.trace && b == 0 && l == 0 && threadIdx.x == 0) { a.trace[0] = t_enter; a.trace[1] = globaltimer_ns(); a.trace[2] = (unsigned long long)a.chunks; }
     if (threadIdx.x == 0) {
-        mbar_init(&sy.full_pack[0], 1); mbar_init(&sy.full_pack[1], 1);
-        mbar_init(&sy.full_unp[0], 1); mbar_init(&sy.full_unp[1], 1);
+        for (int i = 0; i < FZ_NB; ++i) { mbar_init(&sy.full_pack[i], 1); mbar_init(&sy.full_unp[i], 1); }
         sy.packed = 0; sy.reduced = 0; sy.abort = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -155,8 +175,9 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_fuse(const FxLaunch a) {
     const bool avg = a.op == FX_AVG;
     constexpr long long VEC = FX_VEC_BYTES / (long long)sizeof(T);
     const uint32_t cb = (uint32_t)(csz * sizeof(T));            // bytes of one full sub-range chunk
-    unsigned char* pack_buf = fz_dyn;                           // [2][world * cb]
-    unsigned char* unp_buf = fz_dyn + 2ull * world * cb;        // [2][world * cb]
+    unsigned char* pack_buf = fz_dyn;                                   // [FZ_NB][world * cb]
+    unsigned char* unp_buf = fz_dyn + (size_t)FZ_NB * world * cb;       // [FZ_NB][world * cb]
+    unsigned long long* trace = (a.trace && b == 0 && l == 0 && a.chunks <= FZ_TR_CHUNKS) ? a.trace : nullptr;
 
     if (warp == FZ_WARP_POLL) {
         // ------------------------------------------------------------ poll: peers' progress -> smem
@@ -176,6 +197,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_fuse(const FxLaunch a) {
             for (int o = 8; o > 0; o >>= 1) { const uint32_t w = __shfl_xor_sync(0xffffffffu, v, o); v = w < v ? w : v; }
             if (q == 0 && v > published) {
                 st_release_cta(which == FX_FLAG_PACK ? &sy.packed : &sy.reduced, v);
+                if (trace) trace[(which == FX_FLAG_PACK ? FZ_TR_POLLP : FZ_TR_POLLR) + (v - 1)] = globaltimer_ns();
                 published = v;
             }
             if (__all_sync(0xffffffffu, v >= (uint32_t)chunks)) break;
@@ -207,49 +229,62 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_fuse(const FxLaunch a) {
                 __nanosleep(40);
                 continue;
             }
+            if (trace && lane == 0) trace[FZ_TR_SIG + 2 * next] = globaltimer_ns();
             next += adv;
             fence_sys();                                           // the reduce warps' stores, cumulatively
+            if (trace && lane == 0) trace[FZ_TR_SIG + 2 * (next - 1) + 1] = globaltimer_ns();
             if (lane < world) st_relaxed_sys(pipe_flag(a.arena[lane], FX_FLAG_RED, b, rank), base + (uint32_t)next);
         }
     } else if (warp == FZ_WARP_PACK) {
         // ------------------------------------------------------------ pack: tensors -> smem -> arena
-        for (int c = 0; c < chunks; ++c) {
-            const long long c0 = c * csz, c1 = (c0 + csz < slice) ? c0 + csz : slice;
-            const int half = c & 1;
-            unsigned char* buf = pack_buf + (size_t)half * world * cb;
-            if (c >= 2) { if (lane == 0) tma_wait_read1(); __syncwarp(); }      // the stores of chunk c-2 left this half
-            uint32_t tx = 0;
-            bool generic = false;
-            for (int s = 0; s < world; ++s) {
-                const long long lo = s * shard + b * slice + c0, hi = lo + (c1 - c0);
-                unsigned char* sbase = buf + (size_t)s * cb;
-                for_pieces(m, lo, hi, [&](int i, long long p0, long long p1) {
-                    const T* src = static_cast<const T*>(m.in[i]) + (p0 - m.off[i]);
-                    T* dst = reinterpret_cast<T*>(sbase) + (p0 - lo);
-                    const long long n = p1 - p0;
-                    long long bulk = 0;
-                    if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
-                        bulk = n / VEC * VEC;
-                        if (bulk) {
-                            if (lane == 0) tma_load(dst, src, (uint32_t)(bulk * sizeof(T)), &sy.full_pack[half]);
-                            tx += (uint32_t)(bulk * sizeof(T));
-                        }
-                    }
-                    if (bulk < n) {
-                        for (long long e = bulk + lane; e < n; e += 32) dst[e] = src[e];
-                        generic = true;
-                    }
-                });
-            }
-            if (generic) fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_expect_tx(&sy.full_pack[half], tx);
-            if (c >= 1) {                                          // chunk c-1 is in the arena: tell everybody
-                if (lane == 0) tma_wait_all();
+        // Greedy software pipeline over FZ_NB staging buffers: bulk loads run up to FZ_NB - 1 chunks
+        // ahead of the bulk stores, and "chunk c is packed" goes out one chunk behind the stores
+        // (wait_group 1), except for the first and the last chunk, which are drained at once.
+        int L = 0, S = 0;                                          // chunks whose loads / stores are issued
+        while (S < chunks) {
+            if (L < chunks && L - S < FZ_NB - 1) {
+                const int c = L;
+                const long long c0 = c * csz, c1 = (c0 + csz < slice) ? c0 + csz : slice;
+                const int nb = c % FZ_NB;
+                unsigned char* buf = pack_buf + (size_t)nb * world * cb;
+                if (lane == 0) tma_wait_read(FZ_NB - 1 - (L - S));    // the stores of chunk c - FZ_NB left this buffer
                 __syncwarp();
-                signal_packed(a, lane, world, rank, b, base + (uint32_t)c);
+                uint32_t tx = 0;
+                bool generic = false;
+                for (int s = 0; s < world; ++s) {
+                    const long long lo = s * shard + b * slice + c0, hi = lo + (c1 - c0);
+                    unsigned char* sbase = buf + (size_t)s * cb;
+                    for_pieces(m, lo, hi, [&](int i, long long p0, long long p1) {
+                        const T* src = static_cast<const T*>(m.in[i]) + (p0 - m.off[i]);
+                        T* dst = reinterpret_cast<T*>(sbase) + (p0 - lo);
+                        const long long n = p1 - p0;
+                        long long bulk = 0;
+                        if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+                            bulk = n / VEC * VEC;
+                            if (bulk) {
+                                if (lane == 0) tma_load(dst, src, (uint32_t)(bulk * sizeof(T)), &sy.full_pack[nb]);
+                                tx += (uint32_t)(bulk * sizeof(T));
+                            }
+                        }
+                        if (bulk < n) {
+                            for (long long e = bulk + lane; e < n; e += 32) dst[e] = src[e];
+                            generic = true;
+                        }
+                    });
+                }
+                if (generic) fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_expect_tx(&sy.full_pack[nb], tx);
+                if (trace && lane == 0) trace[FZ_TR_PACK + 4 * c + 0] = globaltimer_ns();
+                ++L;
+                continue;
             }
-            mbar_wait(&sy.full_pack[half], (uint32_t)((c >> 1) & 1));
+            const int c = S;
+            const long long c0 = c * csz, c1 = (c0 + csz < slice) ? c0 + csz : slice;
+            const int nb = c % FZ_NB;
+            unsigned char* buf = pack_buf + (size_t)nb * world * cb;
+            mbar_wait(&sy.full_pack[nb], (uint32_t)((c / FZ_NB) & 1));
+            if (trace && lane == 0) trace[FZ_TR_PACK + 4 * c + 1] = globaltimer_ns();
             if (lane == 0) {
                 for (int s = 0; s < world; ++s) {
                     const long long lo = s * shard + b * slice + c0;
@@ -257,28 +292,52 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_fuse(const FxLaunch a) {
                 }
                 tma_commit();
             }
+            ++S;
+            const bool drain = S == 1 || S == chunks;              // keep the first chunk's latency and the tail short
+            if (lane == 0) tma_wait_done(drain ? 0 : 1);
+            __syncwarp();
+            const int ready = drain ? S : S - 1;                   // chunks whose stores have completed
+            if (trace && lane == 0) trace[FZ_TR_PACK + 4 * c + 2] = globaltimer_ns();
+            if (ready > 0) signal_packed(a, lane, world, rank, b, base + (uint32_t)ready);
+            if (trace && lane == 0) trace[FZ_TR_PACK + 4 * c + 3] = globaltimer_ns();
         }
-        if (lane == 0) tma_wait_all();
-        __syncwarp();
-        signal_packed(a, lane, world, rank, b, base + (uint32_t)chunks);
     } else if (warp == FZ_WARP_UNPACK) {
         // ------------------------------------------------------------ unpack: arena -> smem -> tensors
-        for (int c = 0; c < chunks; ++c) {
-            if (!wait_count(&sy.reduced, (uint32_t)c + 1, &sy.abort)) break;
-            const long long c0 = c * csz, c1 = (c0 + csz < slice) ? c0 + csz : slice;
-            const uint32_t bytes = (uint32_t)((c1 - c0) * sizeof(T));
-            const int half = c & 1;
-            unsigned char* buf = unp_buf + (size_t)half * world * cb;
-            if (lane == 0) {
-                if (c >= 2) tma_wait_read1();                      // the stores of chunk c-2 left this half
-                mbar_expect_tx(&sy.full_unp[half], bytes * (uint32_t)world);
-                for (int s = 0; s < world; ++s) {
-                    const long long lo = s * shard + b * slice + c0;
-                    const char* from = (NVLS ? my : a.arena[s]) + region + (unsigned long long)lo * sizeof(T);
-                    tma_load(buf + (size_t)s * cb, from, bytes, &sy.full_unp[half]);
+        // Same greedy pipeline: the bulk loads of a chunk start the moment every shard's part of it is
+        // reduced (up to FZ_NB - 1 chunks ahead); otherwise the oldest landed chunk is stored.
+        int L = 0, S = 0;
+        bool alive = true;
+        while (S < chunks && alive) {
+            const bool can_load = L < chunks && L - S < FZ_NB - 1;
+            const uint32_t seen = __shfl_sync(0xffffffffu, ld_acquire_cta(&sy.reduced), 0);
+            if (can_load && (L == S || seen >= (uint32_t)L + 1)) {
+                if (L == S && !wait_count(&sy.reduced, (uint32_t)L + 1, &sy.abort)) { alive = false; break; }
+                const int c = L;
+                const long long c0 = c * csz, c1 = (c0 + csz < slice) ? c0 + csz : slice;
+                const uint32_t bytes = (uint32_t)((c1 - c0) * sizeof(T));
+                const int nb = c % FZ_NB;
+                unsigned char* buf = unp_buf + (size_t)nb * world * cb;
+                if (trace && lane == 0) trace[FZ_TR_UNPACK + 4 * c + 0] = globaltimer_ns();
+                if (lane == 0) {
+                    tma_wait_read(FZ_NB - 1 - (L - S));            // the stores of chunk c - FZ_NB left this buffer
+                    mbar_expect_tx(&sy.full_unp[nb], bytes * (uint32_t)world);
+                    for (int s = 0; s < world; ++s) {
+                        const long long lo = s * shard + b * slice + c0;
+                        const char* from = (NVLS ? my : a.arena[s]) + region + (unsigned long long)lo * sizeof(T);
+                        tma_load(buf + (size_t)s * cb, from, bytes, &sy.full_unp[nb]);
+                    }
                 }
+                __syncwarp();
+                if (trace && lane == 0) trace[FZ_TR_UNPACK + 4 * c + 1] = globaltimer_ns();
+                ++L;
+                continue;
             }
-            mbar_wait(&sy.full_unp[half], (uint32_t)((c >> 1) & 1));
+            const int c = S;
+            const long long c0 = c * csz, c1 = (c0 + csz < slice) ? c0 + csz : slice;
+            const int nb = c % FZ_NB;
+            const unsigned char* buf = unp_buf + (size_t)nb * world * cb;
+            mbar_wait(&sy.full_unp[nb], (uint32_t)((c / FZ_NB) & 1));
+            if (trace && lane == 0) trace[FZ_TR_UNPACK + 4 * c + 2] = globaltimer_ns();
             for (int s = 0; s < world; ++s) {
                 const long long lo = s * shard + b * slice + c0, hi = lo + (c1 - c0);
                 const unsigned char* sbase = buf + (size_t)s * cb;
@@ -296,14 +355,18 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_fuse(const FxLaunch a) {
             }
             if (lane == 0) tma_commit();
             __syncwarp();
+            if (trace && lane == 0) trace[FZ_TR_UNPACK + 4 * c + 3] = globaltimer_ns();
+            ++S;
         }
-        if (lane == 0) tma_wait_all();
+        if (lane == 0) tma_wait_done(0);
     } else {
         // ------------------------------------------------------------ reduce: one warp per chunk
         const int rw = warp - FZ_WARP_RED0;
         uint32_t mine = 0;
         for (int c = rw; c < chunks; c += FZ_RED_WARPS) {
+            if (trace && lane == 0) trace[FZ_TR_RED + 4 * c + 0] = globaltimer_ns();
             if (!wait_count(&sy.packed, (uint32_t)c + 1, &sy.abort)) break;
+            if (trace && lane == 0) trace[FZ_TR_RED + 4 * c + 1] = globaltimer_ns();
             const long long c0 = c * csz, c1 = (c0 + csz < slice) ? c0 + csz : slice;
             const long long nvec = (c1 - c0) / VEC;
             const unsigned long long byte_off = region + (unsigned long long)(rank * shard + b * slice + c0) * sizeof(T);
@@ -321,10 +384,12 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_fuse(const FxLaunch a) {
                 reduce_vectors<T, W, FX_SUM>(a, world, byte_off, nvec, avg, my, Lane{lane, 32});
             }
             __syncwarp();
+            if (trace && lane == 0) trace[FZ_TR_RED + 4 * c + 2] = globaltimer_ns();
             if (lane == 0) st_release_cta(&sy.red_prog[rw], ++mine);
         }
     }
     __syncthreads();
+    if (trace && threadIdx.x == 0) trace[3] = globaltimer_ns();
     if (threadIdx.x == 0) {
         pad_of(my)->pipe_epoch[b] = base + (uint32_t)chunks;
         if (atomicAdd(&st->finished, 1u) == gridDim.x - 1) {
@@ -342,7 +407,7 @@ int launch_fuse(K kernel, const fx_plan* plan, const FxLaunch& args, size_t smem
     bool seen = false;
     for (int i = 0; i < n_configured; ++i) seen = seen || configured[i] == fn;
     if (!seen) {
-        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 << 10);
+        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 192 << 10);
         if (e != cudaSuccess) return fx_fail(FX_ERR_CUDA, "cudaFuncSetAttribute(k_fuse): %s", cudaGetErrorString(e));
         if (n_configured < 32) configured[n_configured++] = fn;
     }
@@ -368,7 +433,8 @@ int launch_fuse_t(fx_plan* plan, const FxLaunch& a, size_t smem, cudaStream_t s)
 
 }  // namespace
 
-size_t fx_fuse_smem_bytes(int world, long long chunk_bytes) { return 4ull * world * chunk_bytes; }
+size_t fx_fuse_smem_bytes(int world, long long chunk_bytes) { return 2ull * FZ_NB * world * chunk_bytes; }
+size_t fx_fuse_trace_words(void) { return FZ_TR_WORDS; }
 
 int fx_launch_fuse(fx_plan* plan, const FxLaunch& a, cudaStream_t s) {
     if (plan->algo == FX_ALGO_NVLS && !a.mc_arena) return fx_fail(FX_ERR_STATE, "NVLS plan without a multicast mapping");

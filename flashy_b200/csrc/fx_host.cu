@@ -397,6 +397,13 @@ extern "C" int fx_comm_create(int world, int rank0, int n_local, int device, siz
             break;
         }
         *c->status_host = 0;
+        if (env_ll("FLASHY_B200_TRACE", 0) != 0) {
+            const size_t tb = fx_fuse_trace_words() * sizeof(unsigned long long);
+            if (cudaMalloc((void**)&c->trace_dev, tb) != cudaSuccess || cudaMemset(c->trace_dev, 0, tb) != cudaSuccess) {
+                rc = fx_fail(FX_ERR_CUDA, "trace buffer allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+                break;
+            }
+        }
         if (cudaDeviceSynchronize() != cudaSuccess) { rc = fx_fail(FX_ERR_CUDA, "device sync failed"); break; }
         // ---- fd server for VMM handles
         if (c->mem_kind == FX_COMM_MEM_VMM && n_local < world) {
@@ -641,6 +648,19 @@ extern "C" int fx_comm_get_pointers(fx_comm* c, void** arenas, void** mc_base, u
     return FX_OK;
 }
 
+extern "C" int fx_comm_trace_read(fx_comm* c, uint64_t* out, size_t cap_words, size_t* words) {
+    if (!c) return fx_fail(FX_ERR_INVALID, "comm is NULL");
+    const size_t n = fx_fuse_trace_words();
+    if (words) *words = c->trace_dev ? n : 0;
+    if (!out || !c->trace_dev) return FX_OK;
+    if (cap_words < n) return fx_fail(FX_ERR_INVALID, "trace buffer too small (%zu < %zu words)", cap_words, n);
+    FX_CUDA(cudaSetDevice(c->device));
+    FX_CUDA(cudaDeviceSynchronize());
+    FX_CUDA(cudaMemcpy(out, c->trace_dev, n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    FX_CUDA(cudaMemset(c->trace_dev, 0, n * sizeof(uint64_t)));
+    return FX_OK;
+}
+
 extern "C" int fx_comm_poll(fx_comm* c) {
     if (!c) return fx_fail(FX_ERR_INVALID, "comm is NULL");
     if (c->host_only || !c->status_host) return FX_OK;
@@ -667,6 +687,7 @@ extern "C" void fx_comm_destroy(fx_comm* c) {
         for (int r = 0; r < c->world; ++r) arena_release(c, c->arena[r]);
         if (c->status_host) cudaFreeHost(c->status_host);
         if (c->order_event) cudaEventDestroy(c->order_event);
+        if (c->trace_dev) cudaFree(c->trace_dev);
         cudaGetLastError();
     }
     if (c->shm) {
@@ -871,11 +892,12 @@ extern "C" int fx_plan_create(fx_comm* c, int world, const int64_t* numels, int 
     const bool fuse_able = algo != FX_ALGO_ONE_SHOT && dtype == wire_dtype &&
                            (wire_dtype == FX_F32 || wire_dtype == FX_BF16 || wire_dtype == FX_F16);
     if (fuse_able && env_ll("FLASHY_B200_FUSE", 1) != 0) {
-        long long cbytes = env_ll("FLASHY_B200_FUSE_CHUNK", 4096);
+        // one chunk = `world` sub-ranges of cbytes each; by default 32 KiB per chunk and CTA whatever the
+        // world size (the staging buffers of the two copy roles then take 192 KiB of shared memory)
+        long long cbytes = env_ll("FLASHY_B200_FUSE_CHUNK", (32 << 10) / world);
         cbytes = std::max<long long>(FX_SLICE_ALIGN, cbytes / FX_SLICE_ALIGN * FX_SLICE_ALIGN);
-        while (cbytes > FX_SLICE_ALIGN && fx_fuse_smem_bytes(world, cbytes) > (size_t)(160 << 10)) cbytes /= 2;
-        cbytes = cbytes / FX_SLICE_ALIGN * FX_SLICE_ALIGN;
-        if (fx_fuse_smem_bytes(world, cbytes) <= (size_t)(160 << 10)) {
+        while (cbytes > FX_SLICE_ALIGN && fx_fuse_smem_bytes(world, cbytes) > (size_t)(192 << 10)) cbytes -= FX_SLICE_ALIGN;
+        if (fx_fuse_smem_bytes(world, cbytes) <= (size_t)(192 << 10)) {
             p->fuse_chunk = cbytes / (long long)wsize;
             p->fuse_chunks = (int)((p->slice + p->fuse_chunk - 1) / p->fuse_chunk);
         }
@@ -965,6 +987,7 @@ extern "C" void fx_plan_destroy(fx_plan* p) {
         std::lock_guard<std::mutex> lock(c->mu);
         cudaSetDevice(c->device);
         cudaFree(p->d_off); cudaFree(p->d_in); cudaFree(p->d_out); cudaFree(p->d_state);
+        for (void* keep : p->capture_bufs) cudaFreeHost(keep);
         const size_t need = round_up(p->wire_bytes, 256);
         c->free_regions.push_back({p->region[0] - FX_PAD_BYTES, 2 * need});
         size_t freed = 0;
@@ -985,6 +1008,7 @@ static void fill_launch(fx_comm* c, fx_plan* p, FxLaunch& a) {
     a.mc_arena = c->mc_base;
     a.status = c->status_dev;
     a.timeout_ns = c->timeout_ns;
+    a.trace = c->trace_dev;
     a.world = c->world; a.rank0 = c->rank0; a.n_local = c->n_local;
     if (p) {
         a.n = p->n; a.off = p->d_off;
@@ -1009,15 +1033,29 @@ struct PinnedRing {
 static std::mutex g_ring_mu;
 static PinnedRing g_ring;
 
-static int upload_ptrs(void** dst, std::vector<const void*>* shadow_c, std::vector<void*>* shadow_m,
+static int upload_ptrs(fx_plan* p, void** dst, std::vector<const void*>* shadow_c, std::vector<void*>* shadow_m,
                        const void* const* src, size_t nptr, bool* valid, cudaStream_t stream) {
-
+    const size_t bytes = nptr * sizeof(void*);
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess) { cudaGetLastError(); cap = cudaStreamCaptureStatusNone; }
+    if (cap != cudaStreamCaptureStatusNone) {
+        // Inside a stream capture the copy becomes a graph node that re-reads its host source at every
+        // replay: the source must live as long as the plan, not in the recycled ring.  A replayed graph
+        // rewrites the device table behind the shadow's back, so a captured plan uploads on every call.
+        void* keep = nullptr;
+        FX_CUDA(cudaHostAlloc(&keep, round_up(bytes, 256), cudaHostAllocPortable));
+        p->capture_bufs.push_back(keep);
+        memcpy(keep, src, bytes);
+        FX_CUDA(cudaMemcpyAsync(dst, keep, bytes, cudaMemcpyHostToDevice, stream));
+        p->captured = true;
+        *valid = false;
+        return FX_OK;
+    }
     const void* const* cur = shadow_c ? shadow_c->data() : (const void* const*)shadow_m->data();
-    if (*valid && memcmp(cur, src, nptr * sizeof(void*)) == 0) return FX_OK;
+    if (*valid && !p->captured && memcmp(cur, src, bytes) == 0) return FX_OK;
     std::lock_guard<std::mutex> lock(g_ring_mu);
     const int k = g_ring.next;
     g_ring.next = (k + 1) % PinnedRing::K;
-    const size_t bytes = nptr * sizeof(void*);
     if (!g_ring.ev[k]) FX_CUDA(cudaEventCreateWithFlags(&g_ring.ev[k], cudaEventDisableTiming));
     else FX_CUDA(cudaEventSynchronize(g_ring.ev[k]));
     if (g_ring.cap[k] < bytes) {
@@ -1087,8 +1125,8 @@ extern "C" int fx_allreduce(fx_plan* p, int op, const void* const* in_ptrs, void
     int rc = pre_launch(c, p, s);
     if (rc != FX_OK) return rc;
     const size_t nptr = (size_t)c->n_local * p->n;
-    if ((rc = upload_ptrs(p->d_in, &p->h_in, nullptr, in_ptrs, nptr, &p->in_valid, s)) != FX_OK) return rc;
-    if ((rc = upload_ptrs(p->d_out, nullptr, &p->h_out, (const void* const*)out_ptrs, nptr, &p->out_valid, s)) != FX_OK) return rc;
+    if ((rc = upload_ptrs(p, p->d_in, &p->h_in, nullptr, in_ptrs, nptr, &p->in_valid, s)) != FX_OK) return rc;
+    if ((rc = upload_ptrs(p, p->d_out, nullptr, &p->h_out, (const void* const*)out_ptrs, nptr, &p->out_valid, s)) != FX_OK) return rc;
     FxLaunch a;
     fill_launch(c, p, a);
     a.op = op; a.mode = FX_MODE_FUSED;
@@ -1126,7 +1164,7 @@ extern "C" int fx_allreduce_begin(fx_plan* p, int op, const void* const* in_ptrs
     int rc = pre_launch(c, p, s);
     if (rc != FX_OK) return rc;
     const size_t nptr = (size_t)c->n_local * p->n;
-    if ((rc = upload_ptrs(p->d_in, &p->h_in, nullptr, in_ptrs, nptr, &p->in_valid, s)) != FX_OK) return rc;
+    if ((rc = upload_ptrs(p, p->d_in, &p->h_in, nullptr, in_ptrs, nptr, &p->in_valid, s)) != FX_OK) return rc;
     FxLaunch a;
     fill_launch(c, p, a);
     a.op = op; a.mode = FX_MODE_BEGIN;
@@ -1145,7 +1183,7 @@ extern "C" int fx_allreduce_finish(fx_plan* p, void* const* out_ptrs, void* stre
     FX_CUDA(cudaSetDevice(c->device));
     const size_t nptr = (size_t)c->n_local * p->n;
     int rc;
-    if ((rc = upload_ptrs(p->d_out, nullptr, &p->h_out, (const void* const*)out_ptrs, nptr, &p->out_valid, s)) != FX_OK) return rc;
+    if ((rc = upload_ptrs(p, p->d_out, nullptr, &p->h_out, (const void* const*)out_ptrs, nptr, &p->out_valid, s)) != FX_OK) return rc;
     FxLaunch a;
     fill_launch(c, p, a);
     rc = fx_launch_unpack(p, a, s);
@@ -1164,8 +1202,8 @@ extern "C" int fx_broadcast(fx_plan* p, int src, void* const* ptrs, void* stream
     int rc = pre_launch(c, p, s);
     if (rc != FX_OK) return rc;
     const size_t nptr = (size_t)c->n_local * p->n;
-    if ((rc = upload_ptrs(p->d_in, &p->h_in, nullptr, (const void* const*)ptrs, nptr, &p->in_valid, s)) != FX_OK) return rc;
-    if ((rc = upload_ptrs(p->d_out, nullptr, &p->h_out, (const void* const*)ptrs, nptr, &p->out_valid, s)) != FX_OK) return rc;
+    if ((rc = upload_ptrs(p, p->d_in, &p->h_in, nullptr, (const void* const*)ptrs, nptr, &p->in_valid, s)) != FX_OK) return rc;
+    if ((rc = upload_ptrs(p, p->d_out, nullptr, &p->h_out, (const void* const*)ptrs, nptr, &p->out_valid, s)) != FX_OK) return rc;
     FxLaunch a;
     fill_launch(c, p, a);
     a.src = src;

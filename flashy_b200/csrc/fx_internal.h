@@ -59,6 +59,7 @@ struct FxLaunch {
     int mode;                         // FxMode
     int chunks;                       // > 0: pipelined kernel, chunks per slice
     long long chunk_elems;            // elements per chunk (multiple of 128 bytes)
+    unsigned long long* trace;        // FLASHY_B200_TRACE=1: globaltimer stamps of CTA 0 (fx_fuse.cu), else nullptr
 };
 
 // ---------------------------------------------------------------- host objects
@@ -126,6 +127,7 @@ struct fx_comm {
     void* last_stream = nullptr;      // stream of the most recent collective launch (see order_after_previous)
     bool have_last = false;
     cudaEvent_t order_event = nullptr;
+    unsigned long long* trace_dev = nullptr;    // FLASHY_B200_TRACE=1: per-role time stamps of the fused kernel
 };
 
 struct fx_plan {
@@ -151,6 +153,8 @@ struct fx_plan {
     std::vector<void*> h_out;
     bool in_valid = false, out_valid = false;
     bool begun = false;
+    bool captured = false;                      // a launch of this plan was stream-captured (see upload_ptrs)
+    std::vector<void*> capture_bufs;            // pinned pointer tables the captured copy nodes read
 };
 
 // ---------------------------------------------------------------- error plumbing
@@ -173,6 +177,7 @@ int fx_launch_barrier(fx_comm* comm, const FxLaunch& args, cudaStream_t stream);
 // Fused five-role kernel with TMA staging (fx_fuse.cu): float SUM / AVG buckets sent in their own dtype.
 int fx_launch_fuse(fx_plan* plan, const FxLaunch& args, cudaStream_t stream);
 size_t fx_fuse_smem_bytes(int world, long long chunk_bytes);
+size_t fx_fuse_trace_words(void);
 // fx_kernel_id of the kernel an all-reduce of `op` on this plan launches (FUSED mode).
 int fx_plan_kernel_id(const fx_plan* plan, int op);
 // Largest gridDim.x such that gridDim.x * n_local CTAs of the widest kernel are co-resident.

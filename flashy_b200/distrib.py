@@ -41,7 +41,7 @@ __all__ = [
     "rank", "world_size", "init", "rank_zero_only", "is_rank_zero", "is_distributed", "all_reduce",
     "average_metrics", "wrap", "average_tensors", "broadcast_tensors", "broadcast_model",
     "sync_gradients", "eager_sync_gradients", "sync_model", "eager_sync_model", "loader",
-    "broadcast_object", "barrier", "sync_buffers",
+    "broadcast_object", "barrier", "sync_buffers", "overlap",
 ]
 
 
@@ -496,7 +496,7 @@ def sync_buffers(model: torch.nn.Module, average: bool = True) -> None:
 
 
 class _ModelLists:
-    __slots__ = ("params", "buffers", "float_buffers", "age", "fast", "epoch")
+    __slots__ = ("params", "buffers", "float_buffers", "age", "fast", "epoch", "overlap")
 
     def __init__(self, model):
         self.params = list(model.parameters())
@@ -504,6 +504,7 @@ class _ModelLists:
         self.float_buffers = [b for b in self.buffers if b.dtype.is_floating_point or b.dtype.is_complex]
         self.age = 0
         self.epoch = _struct_epoch[0]
+        self.overlap: tp.Optional["_Overlap"] = None    # hook-driven bucket launches (see overlap())
         self.fast: tp.Dict[tp.Any, tp.Any] = {}     # (tag, n) -> (key, layout) of a validated tensor list
 
 
@@ -535,6 +536,8 @@ def _model_entry(model: torch.nn.Module) -> _ModelLists:
     edits that bypass the registration API (``del model.fc``, writes to ``_parameters``)."""
     entry = _model_cache.get(model)
     if entry is None or entry.epoch != _struct_epoch[0] or entry.age >= _MODEL_REVALIDATE:
+        if entry is not None and entry.overlap is not None:
+            entry.overlap.remove()                 # hooks of the stale parameter list
         entry = _ModelLists(model)
         _model_cache[model] = entry
     entry.age += 1
@@ -580,11 +583,15 @@ def sync_model(model: torch.nn.Module, sync_buffers: bool = True, average_buffer
 
     With the default arguments the gradients and the float buffers of one dtype travel in ONE
     bucket, i.e. one kernel launch for the whole model (the reference: one all-reduce and one
-    divide per tensor, in two passes)."""
+    divide per tensor, in two passes).  With backward overlap enabled for ``model`` (``overlap()`` or
+    ``FLASHY_B200_OVERLAP=1``) most of that bucket is already on the wire when this is called."""
     ctx = _context.current()
     if ctx.world == 1:
         return
     entry = _model_entry(model)
+    if ctx.n_local == 1 and (entry.overlap is not None or _overlap_wanted(model)):
+        if _sync_model_overlapped(ctx, model, entry, sync_buffers, average_buffers):
+            return
     grads = [p.grad for p in entry.params]
     for g in grads:
         if g is None:
@@ -596,6 +603,172 @@ def sync_model(model: torch.nn.Module, sync_buffers: bool = True, average_buffer
         _average_cached(ctx, entry, "grads", grads)
         if sync_buffers:
             broadcast_tensors(entry.float_buffers)
+
+
+# ------------------------------------------------------------------------------------------
+# backward overlap for plain ``sync_model`` users (opt-in; an ADDITION to the reference surface)
+# ------------------------------------------------------------------------------------------
+
+_overlap_models: "weakref.WeakKeyDictionary[torch.nn.Module, int]" = weakref.WeakKeyDictionary()
+
+
+def overlap(model: torch.nn.Module, enabled: bool = True, bucket_mb: tp.Optional[float] = None) -> None:
+    """Opt ``model`` into (or out of) backward overlap for ``sync_model``.
+
+    NOT part of the reference surface.  The reference offers overlap only through the
+    ``eager_sync_model`` context manager (flashy/distrib.py:213-224); a solver written as
+    ``loss.backward(); distrib.sync_model(model); optim.step()`` (examples/cifar/solver.py:50-52)
+    exposes the whole exchange.  With overlap enabled, parameters get post-accumulate-grad hooks:
+    gradients are grouped in buckets of ``bucket_mb`` MiB (``FLASHY_B200_OVERLAP_BUCKET_MB``, 8) in
+    the order backward produces them, and a bucket is averaged IN PLACE on the communicator's side
+    stream the moment its last gradient has been accumulated, while backward continues.
+    ``sync_model`` then only sends the tail bucket (the first layers' gradients plus the float
+    buffers) and makes the current stream wait.  The same ``sync_model`` call sites keep working;
+    with several backward passes per ``sync_model`` (gradient accumulation) every pass re-averages,
+    which gives the same mean by linearity.  Only the one-rank-per-process layout overlaps; the
+    setting ``FLASHY_B200_OVERLAP=1`` enables it for every model passed to ``sync_model``."""
+    if enabled:
+        cap = bucket_mb if bucket_mb is not None else float(os.environ.get("FLASHY_B200_OVERLAP_BUCKET_MB", "8"))
+        _overlap_models[model] = max(1, int(cap * (1 << 20)))
+    else:
+        _overlap_models.pop(model, None)
+        entry = _model_cache.get(model)
+        if entry is not None and entry.overlap is not None:
+            entry.overlap.remove()
+            entry.overlap = None
+
+
+def _overlap_wanted(model: torch.nn.Module) -> bool:
+    if model in _overlap_models:
+        return True
+    if os.environ.get("FLASHY_B200_OVERLAP", "0") == "1":
+        overlap(model, True)
+        return True
+    return False
+
+
+class _Overlap:
+    """Hook-driven bucket launches of one model (one-rank-per-process layout)."""
+
+    def __init__(self, ctx, engine: Engine, entry: "_ModelLists", cap: int):
+        self.ctx, self.engine = ctx, engine
+        self.params = [p for p in entry.params if p.requires_grad]
+        # buckets in reverse registration order ~ the order backward yields gradients
+        self.buckets: tp.List[tp.List[int]] = []
+        fill, last_dtype = 0, None
+        for i in range(len(self.params) - 1, -1, -1):
+            p = self.params[i]
+            size = p.numel() * p.element_size()
+            if self.buckets and p.dtype == last_dtype and fill + size <= cap:
+                self.buckets[-1].append(i)
+                fill += size
+            else:
+                self.buckets.append([i])
+                fill, last_dtype = size, p.dtype
+        self.where = {}
+        for k, idxs in enumerate(self.buckets):
+            for i in idxs:
+                self.where[i] = k
+        self.n_hook = len(self.buckets) - 1            # the last (tail) bucket waits for sync_model
+        self.left = [len(b) for b in self.buckets]
+        self.next = 0                                  # next bucket to launch (strictly in order)
+        self.layouts: tp.Dict[tp.Any, tp.Tuple[tp.Any, _Layout]] = {}
+        self.pending = False                           # something is in flight on the side stream
+        self.checked = False
+        self.launched = 0                              # hook launches since the last sync_model
+        self.handles = [p.register_post_accumulate_grad_hook(lambda _p, i=i: self._on_grad(i))
+                        for i, p in enumerate(self.params)]
+
+    def remove(self) -> None:
+        for h in self.handles:
+            h.remove()
+        self.handles = []
+
+    # -- called on the autograd thread ------------------------------------------------------
+    def _on_grad(self, i: int) -> None:
+        k = self.where[i]
+        if k >= self.n_hook:
+            return                                     # tail bucket: sent by sync_model
+        self.left[k] -= 1
+        while self.left[self.next] <= 0:               # strictly in bucket order: same sequence on every rank
+            k = self.next
+            self.left[k] += len(self.buckets[k])
+            self.next = (k + 1) % self.n_hook
+            self.launched += 1
+            self._launch(("hook", k), [self.params[j].grad for j in self.buckets[k]])
+            if self.next == 0:
+                break                                  # every hook bucket of this backward pass is out
+
+    def _launch(self, tag, tensors: tp.List[torch.Tensor]) -> None:
+        """Average ``tensors`` in place on the side stream, ordered after the current stream."""
+        engine, side = self.engine, self.engine.side_stream
+        ptrs = [t.data_ptr() for t in tensors]
+        cached = self.layouts.get(tag)
+        if cached is None or (ptrs != cached[1].last_in and _list_key(tensors) != cached[0]) \
+                or any(b.plan.handle is None for b in cached[1].buckets):
+            key = _list_key(tensors)
+            layout = _layout_for(self.ctx, engine, "ar", tensors, N.FX_AVG, key, lossy=True)
+            self.layouts[tag] = cached = (key, layout)
+        layout = cached[1]
+        if ptrs != layout.last_in:
+            _dense_or_raise(tensors, engine.device)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        side.wait_event(ev)
+        with torch.cuda.stream(side):
+            _run_layout(self.ctx, engine, layout, ptrs, ptrs, N.FX_AVG)
+        self.pending = True
+
+    # -- called from sync_model ---------------------------------------------------------------
+    def finish(self, extra: tp.List[torch.Tensor]) -> None:
+        """Send what the hooks did not (buckets the in-order rule held back, the tail bucket, the
+        float buffers), then make the current stream wait for the side stream."""
+        if self.n_hook:
+            if self.next != 0:
+                late = range(self.next, self.n_hook)   # held back by the in-order rule (a gradient is missing)
+            elif self.launched == 0:
+                late = range(0, self.n_hook)           # nothing went out during backward
+            else:
+                late = range(0)
+            for k in late:
+                got = [self.params[j].grad for j in self.buckets[k] if self.params[j].grad is not None]
+                if got:
+                    self._launch(("late", k, len(got)), got)
+            self.next, self.launched = 0, 0
+            self.left = [len(b) for b in self.buckets]
+        tail = [self.params[j].grad for j in self.buckets[-1] if self.params[j].grad is not None] + extra
+        if tail:
+            self._launch(("tail", len(tail)), tail)
+        if self.pending:
+            done = torch.cuda.Event()
+            done.record(self.engine.side_stream)
+            torch.cuda.current_stream().wait_event(done)
+            self.pending = False
+
+
+def _sync_model_overlapped(ctx, model, entry: "_ModelLists", sync_buffers: bool, average_buffers: bool) -> bool:
+    """The overlap flavour of ``sync_model``; False if overlap cannot be used for this call."""
+    grads = [p.grad for p in entry.params if p.grad is not None]
+    if not grads:
+        return False
+    engine = _engine(ctx, grads)
+    if engine.host_only:
+        return False
+    st = entry.overlap
+    if st is None:
+        # first call: install the hooks (they act from the next backward on) and sync the ordinary way
+        entry.overlap = _Overlap(ctx, engine, entry, _overlap_models[model])
+        return False
+    extra = entry.float_buffers if (sync_buffers and average_buffers) else []
+    if engine.check_mode != "plan" or not st.checked:
+        # one host rendezvous per call, as the reference's count checks (flashy/distrib.py:205-208)
+        total = len(grads) + len(extra)
+        _check_number_of_params(grads + extra, ("overlap", total, len(st.buckets)))
+        st.checked = True
+    st.finish(extra)
+    if sync_buffers and not average_buffers:
+        broadcast_tensors(entry.float_buffers)
+    return True
 
 
 # ------------------------------------------------------------------------------------------

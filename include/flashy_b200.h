@@ -144,6 +144,11 @@ int fx_comm_get_info(fx_comm* comm, fx_comm_info* info);
  * the window the micro-benchmarks under benchmarks/ use to time raw NVLink / multimem rates. */
 int fx_comm_get_pointers(fx_comm* comm, void** arenas, void** mc_base, uint64_t* mc_bytes,
                          uint64_t* pad_bytes);
+/* Diagnostics: with FLASHY_B200_TRACE=1 in the environment at fx_comm_create, CTA 0 of every fused
+ * all-reduce launch (k_fuse) stamps %globaltimer at the hand-offs of its warp roles.  This copies the
+ * stamps of the most recent launch out (`words` = 0 when tracing is off) and clears them;
+ * benchmarks/trace_fuse.py turns them into a per-chunk timeline.  No reference counterpart. */
+int fx_comm_trace_read(fx_comm* comm, uint64_t* out, size_t cap_words, size_t* words);
 /* Asynchronous device-side error state (flag-wait timeout): FX_OK or the sticky error. */
 int fx_comm_poll(fx_comm* comm);
 /* Poison the communicator for every rank of the world: all blocked and future host-side
