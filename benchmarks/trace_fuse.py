@@ -29,6 +29,7 @@ TR_RED = TR_UNPACK + 4 * TR_CHUNKS
 TR_SIG = TR_RED + 4 * TR_CHUNKS
 TR_POLLP = TR_SIG + 2 * TR_CHUNKS
 TR_POLLR = TR_POLLP + TR_CHUNKS
+TR_CTA = TR_POLLR + TR_CHUNKS
 
 
 def main():
@@ -94,8 +95,17 @@ def main():
         def period(key):
             vals = [r[key] for r in rows if r[key] is not None]
             return round((vals[-1] - vals[0]) / max(1, len(vals) - 1), 3) if len(vals) > 1 else None
+        ctas = [(t[TR_CTA + 2 * i], t[TR_CTA + 2 * i + 1]) for i in range(512) if t[TR_CTA + 2 * i]]
+        starts = sorted((a - t0) / 1e3 for a, _ in ctas)
+        ends = sorted((z - t0) / 1e3 for _, z in ctas)
+        durs = sorted((z - a) / 1e3 for a, z in ctas)
+        q = lambda v, f: round(v[min(len(v) - 1, int(f * len(v)))], 1)      # noqa: E731
+        cta = {"n": len(ctas), "start_min_med_max": [q(starts, 0), q(starts, 0.5), q(starts, 1)],
+               "end_min_med_max": [q(ends, 0), q(ends, 0.5), q(ends, 1)],
+               "duration_min_med_max": [q(durs, 0), q(durs, 0.5), q(durs, 1)],
+               "slowest_ctas": sorted(range(len(ctas)), key=lambda i: -(ctas[i][1] - t0))[:6]}
         print(json.dumps({
-            "case": f"{name}/{str(dtype).split('.')[-1]}", "world": world, "bytes": nbytes, "chunks_per_cta": chunks,
+            "case": f"{name}/{str(dtype).split('.')[-1]}", "ctas": cta, "world": world, "bytes": nbytes, "chunks_per_cta": chunks,
             "event_us": round(e0.elapsed_time(e1) * 1e3, 1), "meta_loaded_us": us(t[1]), "exit_us": us(t[3]),
             "period_us": {k: period(k) for k in ("pack_load", "pack_signalled", "all_packed", "red_done", "sig_fenced",
                                                  "all_reduced", "unp_stored")},

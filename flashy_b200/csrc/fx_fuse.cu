@@ -37,6 +37,7 @@ namespace {
 #define FZ_WARP_UNPACK 3
 #define FZ_WARP_RED0 4
 #define FZ_RED_WARPS 4
+#define FZ_UNIT 4096                      // bytes one reduce warp takes at a time (8 vectors per lane)
 
 // ---------------------------------------------------------------------------- shared-memory sync
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -111,7 +112,8 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 #define FZ_TR_SIG (FZ_TR_RED + 4 * FZ_TR_CHUNKS)       // [c][2]: detected, fence done
 #define FZ_TR_POLLP (FZ_TR_SIG + 2 * FZ_TR_CHUNKS)     // [c]: "c+1 chunks packed everywhere" published
 #define FZ_TR_POLLR (FZ_TR_POLLP + FZ_TR_CHUNKS)       // [c]: "c+1 chunks reduced everywhere" published
-#define FZ_TR_WORDS (FZ_TR_POLLR + FZ_TR_CHUNKS)
+#define FZ_TR_CTA (FZ_TR_POLLR + FZ_TR_CHUNKS)         // [b][2]: kernel entry and exit of every CTA (hosted rank 0)
+#define FZ_TR_WORDS (FZ_TR_CTA + 2 * FX_MAX_BLOCKS)
 
 #define FZ_NB 3                             // staging buffers per copy role (chunks in flight)
 struct FuseSync {
@@ -158,7 +160,8 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_fuse(const FxLaunch a) {
     // the two owner-private words this launch depends on, fetched together
     const uint32_t calls = ld_volatile_u32(&st->calls);
     const uint32_t base = ld_volatile_u32(&pad_of(my)->pipe_epoch[b]);
-    const unsigned long long t_enter = (a.trace && b == 0 && l == 0 && threadIdx.x == 0) ? globaltimer_ns() : 0;
+    const unsigned long long t_enter = (a.trace && l == 0 && threadIdx.x == 0) ? globaltimer_ns() : 0;
+    if (a.trace && l == 0 && threadIdx.x == 0) a.trace[FZ_TR_CTA + 2 * b] = t_enter;
     const Meta m = load_meta(a, l, &meta_smem);                 // (contains a __syncthreads)
     if (a.trace && b == 0 && l == 0 && threadIdx.x == 0) { a.trace[0] = t_enter; a.trace[1] = globaltimer_ns(); a.trace[2] = (unsigned long long)a.chunks; }
     if (threadIdx.x == 0) {
@@ -216,22 +219,31 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_fuse(const FxLaunch a) {
         }
     } else if (warp == FZ_WARP_SIG) {
         // ------------------------------------------------------------ signal: reduced chunks -> peers
+        const int upc = (int)((cb + FZ_UNIT - 1) / FZ_UNIT);
         int next = 0;
         while (next < chunks) {
-            const int c = next + lane;
-            bool done = false;
-            if (c < chunks) done = ld_acquire_cta(&sy.red_prog[c % FZ_RED_WARPS]) > (uint32_t)(c / FZ_RED_WARPS);
-            const unsigned mask = __ballot_sync(0xffffffffu, done);
-            const int n = __ffs(~mask) - 1;                        // leading chunks that are complete (32 if all)
-            const int adv = n < 0 ? 32 : n;
-            if (adv == 0) {
+            // lane w < FZ_RED_WARPS: how many chunks (counted from 0) are covered by warp w's finished units
+            int covered = chunks;
+            if (lane < FZ_RED_WARPS) {
+                const long long done = ld_acquire_cta(&sy.red_prog[lane]);          // units finished by warp `lane`
+                // warp w owns units w, w + R, ...: its first `done` units cover all units < done * R + w of its
+                // residue class, i.e. every chunk c with (c + 1) * upc <= done * R + w ... conservatively:
+                const long long upto = done * FZ_RED_WARPS + lane;                  // first unit of this warp NOT done
+                covered = (int)(upto / upc);                                        // chunks entirely below it
+                if (covered > chunks) covered = chunks;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { const int w = __shfl_xor_sync(0xffffffffu, covered, o); covered = w < covered ? w : covered; }
+            if (covered <= next) {
                 if (*reinterpret_cast<const volatile uint32_t*>(&sy.abort)) break;
                 __nanosleep(40);
                 continue;
             }
             if (trace && lane == 0) trace[FZ_TR_SIG + 2 * next] = globaltimer_ns();
-            next += adv;
-            fence_sys();                                           // the reduce warps' stores, cumulatively
+            next = covered;
+            // order the flag behind the reduce warps' stores (cumulative): they went to every peer's arena with
+            // NVLS (system scope), to this GPU's own arena otherwise (GPU scope is enough, see signal_packed)
+            if (NVLS) fence_sys(); else fence_gpu();
             if (trace && lane == 0) trace[FZ_TR_SIG + 2 * (next - 1) + 1] = globaltimer_ns();
             if (lane < world) st_relaxed_sys(pipe_flag(a.arena[lane], FX_FLAG_RED, b, rank), base + (uint32_t)next);
         }
@@ -360,36 +372,49 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_fuse(const FxLaunch a) {
         }
         if (lane == 0) tma_wait_done(0);
     } else {
-        // ------------------------------------------------------------ reduce: one warp per chunk
+        // ------------------------------------------------------------ reduce: 4 KiB units, round-robin over the warps
+        // A chunk of one sub-range is cut into units of FZ_UNIT bytes (one unit = 8 vectors per lane); unit
+        // u = c * upc + j goes to warp u % FZ_RED_WARPS, so the warps share a chunk's latency when chunks
+        // are large (small worlds) and work on different chunks when a chunk is one unit (W = 8).
         const int rw = warp - FZ_WARP_RED0;
+        const long long uvec = FZ_UNIT / FX_VEC_BYTES;
+        const int upc = (int)((cb + FZ_UNIT - 1) / FZ_UNIT);       // units per chunk
+        const long long units = (long long)chunks * upc;
         uint32_t mine = 0;
-        for (int c = rw; c < chunks; c += FZ_RED_WARPS) {
-            if (trace && lane == 0) trace[FZ_TR_RED + 4 * c + 0] = globaltimer_ns();
+        for (long long u = rw; u < units; u += FZ_RED_WARPS) {
+            const int c = (int)(u / upc), j = (int)(u % upc);
+            if (trace && lane == 0 && j == 0) trace[FZ_TR_RED + 4 * c + 0] = globaltimer_ns();
             if (!wait_count(&sy.packed, (uint32_t)c + 1, &sy.abort)) break;
-            if (trace && lane == 0) trace[FZ_TR_RED + 4 * c + 1] = globaltimer_ns();
+            if (trace && lane == 0 && j == 0) trace[FZ_TR_RED + 4 * c + 1] = globaltimer_ns();
             const long long c0 = c * csz, c1 = (c0 + csz < slice) ? c0 + csz : slice;
-            const long long nvec = (c1 - c0) / VEC;
-            const unsigned long long byte_off = region + (unsigned long long)(rank * shard + b * slice + c0) * sizeof(T);
-            if (NVLS) {
-                char* mc = a.mc_arena + byte_off;
-                constexpr int U = 8;
-                for (long long v0 = lane; v0 < nvec; v0 += 32 * U) {
-                    uint4 r[U];
+            const long long cvec = (c1 - c0) / VEC;                 // vectors of this chunk (the last one may be short)
+            const long long v_lo = j * uvec, v_hi = (v_lo + uvec < cvec) ? v_lo + uvec : cvec;
+            if (v_lo < v_hi) {
+                const unsigned long long byte_off = region + (unsigned long long)(rank * shard + b * slice + c0) * sizeof(T)
+                                                    + (unsigned long long)v_lo * FX_VEC_BYTES;
+                const long long nvec = v_hi - v_lo;
+                if (NVLS) {
+                    char* mc = a.mc_arena + byte_off;
+                    constexpr int U = 8;
+                    for (long long v0 = lane; v0 < nvec; v0 += 32 * U) {
+                        uint4 r[U];
 #pragma unroll
-                    for (int k = 0; k < U; ++k) { const long long v = v0 + 32 * k; if (v < nvec) r[k] = Multimem<T>::ld_reduce(mc + v * FX_VEC_BYTES); }
+                        for (int k = 0; k < U; ++k) { const long long v = v0 + 32 * k; if (v < nvec) r[k] = Multimem<T>::ld_reduce(mc + v * FX_VEC_BYTES); }
 #pragma unroll
-                    for (int k = 0; k < U; ++k) { const long long v = v0 + 32 * k; if (v < nvec) multimem_st(mc + v * FX_VEC_BYTES, avg ? scale_vec<T>(r[k], world) : r[k]); }
+                        for (int k = 0; k < U; ++k) { const long long v = v0 + 32 * k; if (v < nvec) multimem_st(mc + v * FX_VEC_BYTES, avg ? scale_vec<T>(r[k], world) : r[k]); }
+                    }
+                } else {
+                    reduce_vectors<T, W, FX_SUM>(a, world, byte_off, nvec, avg, my, Lane{lane, 32});
                 }
-            } else {
-                reduce_vectors<T, W, FX_SUM>(a, world, byte_off, nvec, avg, my, Lane{lane, 32});
             }
             __syncwarp();
-            if (trace && lane == 0) trace[FZ_TR_RED + 4 * c + 2] = globaltimer_ns();
+            if (trace && lane == 0 && j == upc - 1) trace[FZ_TR_RED + 4 * c + 2] = globaltimer_ns();
             if (lane == 0) st_release_cta(&sy.red_prog[rw], ++mine);
         }
     }
     __syncthreads();
     if (trace && threadIdx.x == 0) trace[3] = globaltimer_ns();
+    if (a.trace && l == 0 && threadIdx.x == 0) a.trace[FZ_TR_CTA + 2 * b + 1] = globaltimer_ns();
     if (threadIdx.x == 0) {
         pad_of(my)->pipe_epoch[b] = base + (uint32_t)chunks;
         if (atomicAdd(&st->finished, 1u) == gridDim.x - 1) {

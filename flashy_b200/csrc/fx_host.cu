@@ -1043,7 +1043,11 @@ static int upload_ptrs(fx_plan* p, void** dst, std::vector<const void*>* shadow_
         // replay: the source must live as long as the plan, not in the recycled ring.  A replayed graph
         // rewrites the device table behind the shadow's back, so a captured plan uploads on every call.
         void* keep = nullptr;
-        FX_CUDA(cudaHostAlloc(&keep, round_up(bytes, 256), cudaHostAllocPortable));
+        cudaStreamCaptureMode mode = cudaStreamCaptureModeRelaxed;      // an allocation is "unsafe" under global capture
+        FX_CUDA(cudaThreadExchangeStreamCaptureMode(&mode));
+        const cudaError_t ae = cudaHostAlloc(&keep, round_up(bytes, 256), cudaHostAllocPortable);
+        cudaThreadExchangeStreamCaptureMode(&mode);
+        if (ae != cudaSuccess) return fx_fail(FX_ERR_CUDA, "pinned pointer table for a captured launch: %s", cudaGetErrorString(ae));
         p->capture_bufs.push_back(keep);
         memcpy(keep, src, bytes);
         FX_CUDA(cudaMemcpyAsync(dst, keep, bytes, cudaMemcpyHostToDevice, stream));
