@@ -13,16 +13,16 @@
 //                     chunk, then "chunk c packed" to every peer's flags_pack[b][me]
 //   poll    (1 warp)  reads flags_pack[b][*] / flags_red[b][*] of the own pad and publishes the
 //                     minimum over ranks in shared memory (what every rank has packed / reduced)
-//   reduce  (4 warps) one warp per chunk, chunks round-robin: multimem.ld_reduce of the own
+//   reduce  (4 warps) 1 KiB units of a chunk, round-robin over the warps: multimem.ld_reduce of the own
 //                     shard's sub-range through the NVSwitch, / W, multimem.st to all arenas
 //                     (or, without multicast: pull the W arenas in rank order, write the own one)
 //   signal  (1 warp)  watches the reduce warps' progress in shared memory, fences ONCE at system
 //                     scope and writes "chunks < n of shard me are reduced" to every peer
 //   unpack  (1 warp)  arena (own after NVLS, peers' otherwise) -> shared memory -> output tensors
 //
-// Four reduce warps x 8 vectors per lane keep ~1 K multimem requests in flight per SM: the
-// measured optimum next to the copy traffic (more than ~2 K per SM slows BOTH down: 840 -> 560 GB/s
-// bus in benchmarks/nvls_probe.py).  The reduce warps never execute a system-scope fence (1.75 us each on this system,
+// Four reduce warps x 2 vectors per lane keep 4 KiB of multimem requests in flight per SM: the
+// measured plateau (2 KiB per SM already gives 837 of 841 GB/s bus; 64 KiB per SM drops to 770 and
+// only adds queueing in front of the flags -- profiles/r02_nvls_probe_n8.jsonl).  The reduce warps never execute a system-scope fence (1.75 us each on this system,
 // profiles/r02_nvls_probe_n8.jsonl) and never wait for their own stores: the NVLink stream of a
 // CTA only stalls when a peer is late.  Pieces whose tensor address is not 16-byte aligned and
 // the (< 16 byte) tails of odd-sized tensors go through ordinary loads / stores of the same warp.
@@ -37,7 +37,7 @@ namespace {
 #define FZ_WARP_UNPACK 3
 #define FZ_WARP_RED0 4
 #define FZ_RED_WARPS 4
-#define FZ_UNIT 4096                      // bytes one reduce warp takes at a time (8 vectors per lane)
+#define FZ_UNIT 1024                      // bytes one reduce warp takes at a time (2 vectors per lane in flight)
 
 // ---------------------------------------------------------------------------- shared-memory sync
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -261,9 +261,12 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_fuse(const FxLaunch a) {
                 unsigned char* buf = pack_buf + (size_t)nb * world * cb;
                 if (lane == 0) tma_wait_read(FZ_NB - 1 - (L - S));    // the stores of chunk c - FZ_NB left this buffer
                 __syncwarp();
+                // lane s enumerates sub-range s (the pieces of the W sub-ranges are independent): bulk loads
+                // for every piece whose source is 16-byte aligned; odd pieces and tails are left to pass 2
                 uint32_t tx = 0;
                 bool generic = false;
-                for (int s = 0; s < world; ++s) {
+                if (lane < world) {
+                    const int s = lane;
                     const long long lo = s * shard + b * slice + c0, hi = lo + (c1 - c0);
                     unsigned char* sbase = buf + (size_t)s * cb;
                     for_pieces(m, lo, hi, [&](int i, long long p0, long long p1) {
@@ -274,17 +277,30 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_fuse(const FxLaunch a) {
                         if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
                             bulk = n / VEC * VEC;
                             if (bulk) {
-                                if (lane == 0) tma_load(dst, src, (uint32_t)(bulk * sizeof(T)), &sy.full_pack[nb]);
+                                tma_load(dst, src, (uint32_t)(bulk * sizeof(T)), &sy.full_pack[nb]);
                                 tx += (uint32_t)(bulk * sizeof(T));
                             }
                         }
-                        if (bulk < n) {
-                            for (long long e = bulk + lane; e < n; e += 32) dst[e] = src[e];
-                            generic = true;
-                        }
+                        if (bulk < n) generic = true;
                     });
                 }
-                if (generic) fence_proxy_async_smem();
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) tx += __shfl_xor_sync(0xffffffffu, tx, o);
+                if (__any_sync(0xffffffffu, generic)) {
+                    // pass 2 (rare): the whole warp copies what the bulk loads could not take
+                    for (int s = 0; s < world; ++s) {
+                        const long long lo = s * shard + b * slice + c0, hi = lo + (c1 - c0);
+                        unsigned char* sbase = buf + (size_t)s * cb;
+                        for_pieces(m, lo, hi, [&](int i, long long p0, long long p1) {
+                            const T* src = static_cast<const T*>(m.in[i]) + (p0 - m.off[i]);
+                            T* dst = reinterpret_cast<T*>(sbase) + (p0 - lo);
+                            const long long n = p1 - p0;
+                            const long long bulk = (reinterpret_cast<uintptr_t>(src) & 15) == 0 ? n / VEC * VEC : 0;
+                            for (long long e = bulk + lane; e < n; e += 32) dst[e] = src[e];
+                        });
+                    }
+                    fence_proxy_async_smem();
+                }
                 __syncwarp();
                 if (lane == 0) mbar_expect_tx(&sy.full_pack[nb], tx);
                 if (trace && lane == 0) trace[FZ_TR_PACK + 4 * c + 0] = globaltimer_ns();
@@ -330,8 +346,9 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_fuse(const FxLaunch a) {
                 const int nb = c % FZ_NB;
                 unsigned char* buf = unp_buf + (size_t)nb * world * cb;
                 if (trace && lane == 0) trace[FZ_TR_UNPACK + 4 * c + 0] = globaltimer_ns();
+                if (lane < world) tma_wait_read(FZ_NB - 1 - (L - S));  // lane s stored sub-range s of chunk c - FZ_NB from this buffer
+                __syncwarp();
                 if (lane == 0) {
-                    tma_wait_read(FZ_NB - 1 - (L - S));            // the stores of chunk c - FZ_NB left this buffer
                     mbar_expect_tx(&sy.full_unp[nb], bytes * (uint32_t)world);
                     for (int s = 0; s < world; ++s) {
                         const long long lo = s * shard + b * slice + c0;
@@ -350,7 +367,10 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_fuse(const FxLaunch a) {
             const unsigned char* buf = unp_buf + (size_t)nb * world * cb;
             mbar_wait(&sy.full_unp[nb], (uint32_t)((c / FZ_NB) & 1));
             if (trace && lane == 0) trace[FZ_TR_UNPACK + 4 * c + 2] = globaltimer_ns();
-            for (int s = 0; s < world; ++s) {
+            // lane s stores the pieces of sub-range s (one bulk group per lane and chunk)
+            bool generic = false;
+            if (lane < world) {
+                const int s = lane;
                 const long long lo = s * shard + b * slice + c0, hi = lo + (c1 - c0);
                 const unsigned char* sbase = buf + (size_t)s * cb;
                 for_pieces(m, lo, hi, [&](int i, long long p0, long long p1) {
@@ -360,22 +380,35 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_fuse(const FxLaunch a) {
                     long long bulk = 0;
                     if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
                         bulk = n / VEC * VEC;
-                        if (bulk && lane == 0) tma_store(dst, src, (uint32_t)(bulk * sizeof(T)));
+                        if (bulk) tma_store(dst, src, (uint32_t)(bulk * sizeof(T)));
                     }
-                    for (long long e = bulk + lane; e < n; e += 32) dst[e] = src[e];
+                    if (bulk < n) generic = true;
                 });
+                tma_commit();
             }
-            if (lane == 0) tma_commit();
+            if (__any_sync(0xffffffffu, generic)) {
+                for (int s = 0; s < world; ++s) {
+                    const long long lo = s * shard + b * slice + c0, hi = lo + (c1 - c0);
+                    const unsigned char* sbase = buf + (size_t)s * cb;
+                    for_pieces(m, lo, hi, [&](int i, long long p0, long long p1) {
+                        T* dst = static_cast<T*>(m.out[i]) + (p0 - m.off[i]);
+                        const T* src = reinterpret_cast<const T*>(sbase) + (p0 - lo);
+                        const long long n = p1 - p0;
+                        const long long bulk = (reinterpret_cast<uintptr_t>(dst) & 15) == 0 ? n / VEC * VEC : 0;
+                        for (long long e = bulk + lane; e < n; e += 32) dst[e] = src[e];
+                    });
+                }
+            }
             __syncwarp();
             if (trace && lane == 0) trace[FZ_TR_UNPACK + 4 * c + 3] = globaltimer_ns();
             ++S;
         }
-        if (lane == 0) tma_wait_done(0);
+        if (lane < world) tma_wait_done(0);
     } else {
-        // ------------------------------------------------------------ reduce: 4 KiB units, round-robin over the warps
-        // A chunk of one sub-range is cut into units of FZ_UNIT bytes (one unit = 8 vectors per lane); unit
+        // ------------------------------------------------------------ reduce: 1 KiB units, round-robin over the warps
+        // A chunk of one sub-range is cut into units of FZ_UNIT bytes (one unit = 2 vectors per lane); unit
         // u = c * upc + j goes to warp u % FZ_RED_WARPS, so the warps share a chunk's latency when chunks
-        // are large (small worlds) and work on different chunks when a chunk is one unit (W = 8).
+        // are large (small worlds) and a chunk's latency is one batch of loads per warp.
         const int rw = warp - FZ_WARP_RED0;
         const long long uvec = FZ_UNIT / FX_VEC_BYTES;
         const int upc = (int)((cb + FZ_UNIT - 1) / FZ_UNIT);       // units per chunk
@@ -395,7 +428,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_fuse(const FxLaunch a) {
                 const long long nvec = v_hi - v_lo;
                 if (NVLS) {
                     char* mc = a.mc_arena + byte_off;
-                    constexpr int U = 8;
+                    constexpr int U = FZ_UNIT / FX_VEC_BYTES / 32;
                     for (long long v0 = lane; v0 < nvec; v0 += 32 * U) {
                         uint4 r[U];
 #pragma unroll

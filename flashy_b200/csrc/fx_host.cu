@@ -154,7 +154,28 @@ struct FxBlob {
     char shm[64];
     unsigned char uuid[16];
     cudaIpcMemHandle_t ipc[FX_MAX_WORLD];
+    uint64_t host_id;                 // hash of (hostname, boot id): all ranks must share one host
+    char hostname[64];
 };
+
+// Identity of the machine this process runs on.  The arenas are exchanged by fd passing over an
+// abstract unix socket (or cudaIpc) and the count check lives in POSIX shared memory: both only
+// exist inside one host.  FLASHY_B200_HOST_ID overrides the value (tests).
+static uint64_t host_identity(char* name, size_t cap) {
+    memset(name, 0, cap);
+    if (gethostname(name, cap - 1) != 0) snprintf(name, cap, "unknown");
+    const char* forced = getenv("FLASHY_B200_HOST_ID");
+    if (forced && *forced) snprintf(name, cap, "%s", forced);
+    unsigned long long h = 1469598103934665603ull;
+    for (const char* p = name; *p; ++p) { h ^= (unsigned char)*p; h *= 1099511628211ull; }
+    if (!(forced && *forced)) {
+        char boot[64] = {0};
+        FILE* f = fopen("/proc/sys/kernel/random/boot_id", "r");
+        if (f) { if (!fgets(boot, sizeof(boot), f)) boot[0] = 0; fclose(f); }
+        for (const char* p = boot; *p; ++p) { h ^= (unsigned char)*p; h *= 1099511628211ull; }
+    }
+    return h;
+}
 
 // ============================================================================ fd passing over an abstract unix socket
 static int send_fd(int sock, int fd) {
@@ -443,6 +464,7 @@ extern "C" int fx_comm_export(fx_comm* c, void* blob, size_t cap, size_t* len) {
     b.arena_total = c->host_only ? 0 : c->arena[c->rank0].bytes;
     memcpy(b.sock, c->sock_name, sizeof(b.sock));
     memcpy(b.shm, c->shm_name, sizeof(b.shm));
+    b.host_id = host_identity(b.hostname, sizeof(b.hostname));
     if (!c->host_only) {
         cudaDeviceProp prop;
         FX_CUDA(cudaGetDeviceProperties(&prop, c->device));
@@ -473,6 +495,14 @@ extern "C" int fx_comm_connect(fx_comm* c, const void* blobs, size_t blob_len, i
         covered += b.n_local;
     }
     if (covered != c->world) return fx_fail(FX_ERR_INVALID, "blobs cover %d ranks, world is %d", covered, c->world);
+    // One NVSwitch domain = one host: refuse a world that spans machines instead of failing
+    // later in fd passing / shm_open with an unrelated message.
+    for (int p = 1; p < n_procs; ++p) {
+        if (all[p].host_id != all[0].host_id)
+            return fx_fail(FX_ERR_UNSUPPORTED, "ranks span several hosts (rank %d is on '%.63s', rank %d on '%.63s'): flashy_b200 "
+                           "moves data over NVLink inside ONE NVSwitch domain; run one job per node or use torch.distributed "
+                           "(NCCL) for multi-node worlds", all[0].rank0, all[0].hostname, all[p].rank0, all[p].hostname);
+    }
     // ---- rendezvous shm (created by the process hosting rank 0)
     if (!c->shm) {
         const char* name = all[0].shm;

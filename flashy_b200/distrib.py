@@ -12,7 +12,7 @@ bootstrap this module does not touch NCCL/gloo.  There is no CPU / gloo fallback
 data: CPU tensors in a distributed collective raise.
 
 Environment knobs (none of them changes a public signature):
-``FLASHY_B200_ARENA_MB`` (512), ``FLASHY_B200_BUCKET_MB`` (64), ``FLASHY_B200_EAGER_BUCKET_MB`` (8),
+``FLASHY_B200_ARENA_MB`` (1024), ``FLASHY_B200_BUCKET_MB`` (128), ``FLASHY_B200_EAGER_BUCKET_MB`` (8),
 ``FLASHY_B200_ONE_SHOT_MAX`` (bytes, 262144), ``FLASHY_B200_SLICE_BYTES`` (8192),
 ``FLASHY_B200_WIRE=bf16`` (send fp32 gradients as bf16: opt-in, lossy),
 ``FLASHY_B200_CHECK=always|plan`` (count check every call, or only when a bucket plan is new).
@@ -536,10 +536,17 @@ def _model_entry(model: torch.nn.Module) -> _ModelLists:
     edits that bypass the registration API (``del model.fc``, writes to ``_parameters``)."""
     entry = _model_cache.get(model)
     if entry is None or entry.epoch != _struct_epoch[0] or entry.age >= _MODEL_REVALIDATE:
-        if entry is not None and entry.overlap is not None:
-            entry.overlap.remove()                 # hooks of the stale parameter list
-        entry = _ModelLists(model)
-        _model_cache[model] = entry
+        fresh = _ModelLists(model)
+        if entry is not None and len(fresh.params) == len(entry.params) and len(fresh.buffers) == len(entry.buffers) \
+                and all(a is b for a, b in zip(fresh.params, entry.params)) \
+                and all(a is b for a, b in zip(fresh.buffers, entry.buffers)):
+            # some OTHER module was built or edited since: this model is unchanged, keep its layouts and hooks
+            entry.epoch, entry.age = fresh.epoch, 0
+        else:
+            if entry is not None and entry.overlap is not None:
+                entry.overlap.remove()             # hooks of the stale parameter list
+            entry = fresh
+            _model_cache[model] = entry
     entry.age += 1
     return entry
 

@@ -78,7 +78,7 @@ class Engine:
             self.device = -1
         else:
             self.device = torch.cuda.current_device() if device is None else device
-        arena = (arena_mb if arena_mb is not None else _env_int("FLASHY_B200_ARENA_MB", 512)) << 20
+        arena = (arena_mb if arena_mb is not None else _env_int("FLASHY_B200_ARENA_MB", 1024)) << 20
         self.comm = C.c_void_p()
         self.multicast_error: tp.Optional[str] = None
         self._create(arena, N.FX_COMM_HOST_ONLY if self.host_only else N.FX_COMM_MEM_AUTO)
@@ -88,7 +88,7 @@ class Engine:
         N.check(N.lib.fx_comm_get_info(self.comm, C.byref(self.info)))
         self.plans: tp.Dict[tp.Any, Plan] = {}
         self.lock = threading.RLock()
-        self.bucket_cap = min(_env_int("FLASHY_B200_BUCKET_MB", 64) << 20, arena // 8)
+        self.bucket_cap = min(_env_int("FLASHY_B200_BUCKET_MB", 128) << 20, arena // 8)
         self.check_mode = os.environ.get("FLASHY_B200_CHECK", "always")
         self.wire_bf16 = os.environ.get("FLASHY_B200_WIRE", "") == "bf16"
         self.side_stream = None if self.host_only else torch.cuda.Stream(device=self.device)
