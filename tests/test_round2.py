@@ -109,9 +109,13 @@ def test_eager_buckets_of_identical_shape_do_not_share_a_plan(monkeypatch):
     world = 4
     dims = 640                                                       # 640*640*4 B = 1.6 MB > the 1 MB cap
 
-    def make():
-        torch.manual_seed(3)
-        return nn.Sequential(*[nn.Linear(dims, dims, bias=False) for _ in range(4)])
+    torch.manual_seed(3)
+    init = nn.Sequential(*[nn.Linear(dims, dims, bias=False) for _ in range(4)]).state_dict()
+
+    def make():                                                      # (the global RNG is not thread-safe: load a fixed state)
+        m = nn.Sequential(*[nn.Linear(dims, dims, bias=False) for _ in range(4)])
+        m.load_state_dict(init)
+        return m
     gens = [torch.Generator().manual_seed(40 + r) for r in range(world)]
     xs = [torch.randn(8, dims, generator=g) for g in gens]
     grads = []
