@@ -32,6 +32,8 @@ def main():
     ap.add_argument("--no-nccl", action="store_true")
     ap.add_argument("--only-sync", action="store_true", help="skip the flat all_reduce sweep")
     ap.add_argument("--tag", default="")
+    ap.add_argument("--variants", default="", help="';'-separated env settings, e.g. 'FLASHY_B200_FUSE_DEPTH=4;FLASHY_B200_FUSE=0': "
+                    "the sync_model cases are repeated under each (plans are rebuilt in between)")
     args = ap.parse_args()
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
@@ -40,6 +42,7 @@ def main():
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     dist.init_process_group("cpu:gloo,cuda:nccl", init_method="env://")
     from flashy_b200 import distrib
+    from flashy_b200 import _native as N
     from flashy_b200 import context as fctx
     from oracle.refdistrib import RefDistrib
 
@@ -111,27 +114,65 @@ def main():
 
     # ------------------------------------------------------------------ sync_model sized buckets
     import torchvision
-    for name, ctor in (("resnet18", lambda: torchvision.models.resnet18(num_classes=10)),
-                       ("resnet50", torchvision.models.resnet50)):
-        for dtype in (torch.bfloat16, torch.float32):
-            torch.manual_seed(1234)
-            model = ctor().to(dev).to(dtype)
-            for p in model.parameters():
-                p.grad = torch.randn_like(p) * 1e-2
-            nbytes = sum(p.numel() for p in model.parameters()) * dtype.itemsize
-            ours = timeit(lambda: distrib.sync_model(model), args.iters)
-            grads_only = timeit(lambda: distrib.sync_gradients(model.parameters()), args.iters)
-            kern = kernel_ms(lambda: distrib.sync_model(model), args.iters)
-            row = dict(kind="sync_model", model=name, dtype=str(dtype).split(".")[-1], grad_bytes=nbytes, world=world,
-                       ours_ms=ours, ours_grads_only_ms=grads_only, ours_bus_gbs=bus(nbytes, ours),
-                       ours_kernel_ms=kern, ours_kernel_bus_gbs=bus(nbytes, kern))
-            if not args.no_nccl:
-                ref = timeit(lambda: RefDistrib.sync_model(model), max(5, args.iters // 2))
-                flat = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
-                one = timeit(lambda: dist.all_reduce(flat), args.iters)
-                row.update(reference_path_nccl_ms=ref, nccl_flat_ms=one, nccl_flat_bus_gbs=bus(nbytes, one))
-            emit(**row)
-            del model
+
+    def drop_plans():
+        """Collective: forget every cached plan / layout so that the next call re-plans under the current env."""
+        from flashy_b200 import distrib as D
+        torch.cuda.synchronize()
+        dist.barrier()
+        eng = fctx.current().engine
+        for plan in eng.plans.values():
+            plan.destroy()
+        eng.plans.clear()
+        eng.layouts.clear()
+        eng.fast_lists.clear()
+        for entry in list(D._model_cache.values()):
+            entry.fast.clear()
+        dist.barrier()
+
+    variants = [v for v in args.variants.split(";") if v] if args.variants else [""]
+    for variant in variants:
+        saved = {}
+        for kv in [x for x in variant.split(",") if x]:
+            k, v = kv.split("=", 1)
+            saved[k] = os.environ.get(k)
+            os.environ[k] = v
+        if args.variants:
+            drop_plans()
+        for name, ctor in (("resnet18", lambda: torchvision.models.resnet18(num_classes=10)),
+                           ("resnet50", torchvision.models.resnet50)):
+            for dtype in (torch.bfloat16, torch.float32):
+                torch.manual_seed(1234)
+                model = ctor().to(dev).to(dtype)
+                for p in model.parameters():
+                    p.grad = torch.randn_like(p) * 1e-2
+                params = list(model.parameters())
+                nbytes = sum(p.numel() for p in params) * dtype.itemsize
+                ours = timeit(lambda: distrib.sync_model(model), args.iters)
+                grads_only = timeit(lambda: distrib.sync_gradients(model.parameters()), args.iters)
+                grads_list = timeit(lambda: distrib.sync_gradients(params), args.iters)
+                kern = kernel_ms(lambda: distrib.sync_model(model), args.iters)
+                eng = fctx.current().engine
+                big = max(eng.plans.values(), key=lambda pl: pl.info.wire_bytes)
+                row = dict(kind="sync_model", model=name, dtype=str(dtype).split(".")[-1], grad_bytes=nbytes, world=world,
+                           variant=variant, kernel=N.KERNEL_NAMES.get(int(big.info.kernel)), chunks=int(big.info.chunks),
+                           chunk_bytes=int(big.info.chunk_bytes), grid=int(big.info.grid_x),
+                           ours_ms=ours, ours_grads_only_ms=grads_only, ours_grads_list_ms=grads_list, ours_bus_gbs=bus(nbytes, ours),
+                           ours_kernel_ms=kern, ours_kernel_bus_gbs=bus(nbytes, kern))
+                if not args.no_nccl and variant == variants[0]:
+                    ref = timeit(lambda: RefDistrib.sync_model(model), max(5, args.iters // 2))
+                    flat = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
+                    one = timeit(lambda: dist.all_reduce(flat), args.iters)
+                    row.update(reference_path_nccl_ms=ref, nccl_flat_ms=one, nccl_flat_bus_gbs=bus(nbytes, one))
+                emit(**row)
+                del model, params
+                if args.variants:
+                    drop_plans()
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
     eng = fctx.current().engine
     emit(kind="info", native_launches=eng.native_launches(), mem_kind=int(eng.info.mem_kind), world=world,
          max_blocks=int(eng.info.max_blocks), nvls=bool(eng.multicast), nvls_error=eng.multicast_error,

@@ -37,7 +37,6 @@ namespace {
 #define FZ_WARP_UNPACK 3
 #define FZ_WARP_RED0 4
 #define FZ_RED_WARPS 4
-#define FZ_UNIT 1024                      // bytes one reduce warp takes at a time (2 vectors per lane in flight)
 
 // ---------------------------------------------------------------------------- shared-memory sync
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -145,7 +144,8 @@ __device__ __forceinline__ void for_pieces(const Meta& m, long long lo, long lon
     }
 }
 
-template <typename T, bool NVLS, int W>
+// U: 16-byte vectors per lane a reduce warp keeps in flight (one unit = 32 * U vectors).
+template <typename T, bool NVLS, int W, int U>
 __global__ void __launch_bounds__(FZ_THREADS, 1) k_fuse(const FxLaunch a) {
     extern __shared__ __align__(128) unsigned char fz_dyn[];
     __shared__ MetaSmem meta_smem;
@@ -219,6 +219,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_fuse(const FxLaunch a) {
         }
     } else if (warp == FZ_WARP_SIG) {
         // ------------------------------------------------------------ signal: reduced chunks -> peers
+        constexpr uint32_t FZ_UNIT = 32 * U * FX_VEC_BYTES;
         const int upc = (int)((cb + FZ_UNIT - 1) / FZ_UNIT);
         int next = 0;
         while (next < chunks) {
@@ -410,7 +411,8 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_fuse(const FxLaunch a) {
         // u = c * upc + j goes to warp u % FZ_RED_WARPS, so the warps share a chunk's latency when chunks
         // are large (small worlds) and a chunk's latency is one batch of loads per warp.
         const int rw = warp - FZ_WARP_RED0;
-        const long long uvec = FZ_UNIT / FX_VEC_BYTES;
+        constexpr long long uvec = 32 * U;                          // vectors per unit
+        constexpr uint32_t FZ_UNIT = 32 * U * FX_VEC_BYTES;         // bytes per unit
         const int upc = (int)((cb + FZ_UNIT - 1) / FZ_UNIT);       // units per chunk
         const long long units = (long long)chunks * upc;
         uint32_t mine = 0;
@@ -428,7 +430,6 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_fuse(const FxLaunch a) {
                 const long long nvec = v_hi - v_lo;
                 if (NVLS) {
                     char* mc = a.mc_arena + byte_off;
-                    constexpr int U = FZ_UNIT / FX_VEC_BYTES / 32;
                     for (long long v0 = lane; v0 < nvec; v0 += 32 * U) {
                         uint4 r[U];
 #pragma unroll
@@ -480,13 +481,20 @@ int launch_fuse(K kernel, const fx_plan* plan, const FxLaunch& args, size_t smem
 
 template <typename T>
 int launch_fuse_t(fx_plan* plan, const FxLaunch& a, size_t smem, cudaStream_t s) {
-    if (plan->algo == FX_ALGO_NVLS) return launch_fuse(k_fuse<T, true, 0>, plan, a, smem, s);
-    switch (a.world) {
-        case 2: return launch_fuse(k_fuse<T, false, 2>, plan, a, smem, s);
-        case 4: return launch_fuse(k_fuse<T, false, 4>, plan, a, smem, s);
-        case 8: return launch_fuse(k_fuse<T, false, 8>, plan, a, smem, s);
+    if (plan->algo == FX_ALGO_NVLS) {
+        switch (plan->fuse_unroll) {               // FLASHY_B200_FUSE_DEPTH: multimem vectors in flight per lane
+            case 1: return launch_fuse(k_fuse<T, true, 0, 1>, plan, a, smem, s);
+            case 4: return launch_fuse(k_fuse<T, true, 0, 4>, plan, a, smem, s);
+            case 8: return launch_fuse(k_fuse<T, true, 0, 8>, plan, a, smem, s);
+            default: return launch_fuse(k_fuse<T, true, 0, 2>, plan, a, smem, s);
+        }
     }
-    return launch_fuse(k_fuse<T, false, 0>, plan, a, smem, s);
+    switch (a.world) {
+        case 2: return launch_fuse(k_fuse<T, false, 2, 2>, plan, a, smem, s);
+        case 4: return launch_fuse(k_fuse<T, false, 4, 2>, plan, a, smem, s);
+        case 8: return launch_fuse(k_fuse<T, false, 8, 2>, plan, a, smem, s);
+    }
+    return launch_fuse(k_fuse<T, false, 0, 2>, plan, a, smem, s);
 }
 
 }  // namespace

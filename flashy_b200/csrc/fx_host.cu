@@ -929,6 +929,8 @@ extern "C" int fx_plan_create(fx_comm* c, int world, const int64_t* numels, int 
         while (cbytes > FX_SLICE_ALIGN && fx_fuse_smem_bytes(world, cbytes) > (size_t)(192 << 10)) cbytes -= FX_SLICE_ALIGN;
         if (fx_fuse_smem_bytes(world, cbytes) <= (size_t)(192 << 10)) {
             p->fuse_chunk = cbytes / (long long)wsize;
+            const long long depth = env_ll("FLASHY_B200_FUSE_DEPTH", 2);
+            p->fuse_unroll = (depth == 1 || depth == 4 || depth == 8) ? (int)depth : 2;
             p->fuse_chunks = (int)((p->slice + p->fuse_chunk - 1) / p->fuse_chunk);
         }
     }

@@ -140,6 +140,7 @@ struct fx_plan {
     long long chunk = 0;
     int fuse_chunks = 0;                        // fused TMA kernel (fx_fuse.cu): chunks per slice (0 = not eligible)
     long long fuse_chunk = 0;                   // elements per chunk of one sub-range
+    int fuse_unroll = 2;                        // NVLS: 16-byte multimem requests per lane in flight (1, 2, 4, 8)
     size_t esize = 0, wsize = 0, wire_bytes = 0;
     size_t region[2] = {0, 0};
     bool recycled = false;                      // region memory was used by an earlier plan

@@ -770,7 +770,7 @@ def _sync_model_overlapped(ctx, model, entry: "_ModelLists", sync_buffers: bool,
     if engine.check_mode != "plan" or not st.checked:
         # one host rendezvous per call, as the reference's count checks (flashy/distrib.py:205-208)
         total = len(grads) + len(extra)
-        _check_number_of_params(grads + extra, ("overlap", total, len(st.buckets)))
+        _check_number_of_params(grads + extra, (0x6F766C70, total, len(st.buckets)))   # ints only: str hashes differ per process
         st.checked = True
     st.finish(extra)
     if sync_buffers and not average_buffers:

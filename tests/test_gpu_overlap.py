@@ -98,7 +98,10 @@ def _worker(rank, world, nvls_env):
     keep, mean, cols = _expected(world, dev, init, 2, 10)
     params = list(model.parameters())
     for j, i in enumerate(keep):
-        assert _close(params[i].grad.cpu(), mean[j], [c[j] for c in cols], False), i
+        # intermediate values (mean of pass 1 + local pass 2) are rounded where the oracle sums first: bound the
+        # error by the magnitudes that were actually added, not by the (possibly cancelling) total
+        got, scale = params[i].grad.cpu(), max(float(c[j].abs().max()) for c in cols)
+        assert float((got - mean[j]).abs().max()) <= 8 * torch.finfo(torch.float32).eps * max(scale, 1e-30), i
 
     # ---- a module that gets no gradient in this step (the in-order rule holds its bucket back)
     model.zero_grad(set_to_none=True)
