@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--no-nccl", action="store_true")
     ap.add_argument("--only-sync", action="store_true", help="skip the flat all_reduce sweep")
     ap.add_argument("--tag", default="")
+    ap.add_argument("--symm", action="store_true", help="also time torch.ops.symm_mem.{multimem,two_shot,one_shot}_all_reduce")
     ap.add_argument("--variants", default="", help="';'-separated env settings, e.g. 'FLASHY_B200_FUSE_DEPTH=4;FLASHY_B200_FUSE=0': "
                     "the sync_model cases are repeated under each (plans are rebuilt in between)")
     args = ap.parse_args()
@@ -90,6 +91,37 @@ def main():
 
     bus = lambda nbytes, ms: 2 * (world - 1) / world * nbytes / (ms * 1e-3) / 1e9   # noqa: E731
 
+    # ------------------------------------------------------------------ torch.ops.symm_mem comparators
+    symm = {"error": None}
+    if not args.symm:
+        symm["error"] = "not requested (--symm)"
+    elif not args.no_nccl and not args.only_sync:
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            group = dist.group.WORLD
+            pool = symm_mem.empty(min(args.max_mb, 1024) << 20, dtype=torch.uint8, device=dev)
+            symm_mem.rendezvous(pool, group=group)
+            symm.update(pool=pool, name=group.group_name)
+        except Exception as err:      # noqa: BLE001 - comparator only
+            symm["error"] = f"{type(err).__name__}: {err}"[:200]
+
+    def symm_times(nbytes, dtype, iters):
+        """ms of PyTorch's own symmetric-memory all-reduces on the same bytes, or the reason they did not run."""
+        if symm["error"] is not None:
+            return {} if not args.symm else {"symm_mem_error": symm["error"]}
+        out = {}
+        view = symm["pool"][:nbytes].view(dtype)
+        ops = {"symm_multimem_ms": lambda: torch.ops.symm_mem.multimem_all_reduce_(view, "sum", symm["name"]),
+               "symm_two_shot_ms": lambda: torch.ops.symm_mem.two_shot_all_reduce_(view, "sum", symm["name"])}
+        if nbytes <= (1 << 20):
+            ops["symm_one_shot_ms"] = lambda: torch.ops.symm_mem.one_shot_all_reduce(view, "sum", symm["name"])
+        for key, fn in ops.items():
+            try:
+                out[key] = timeit(fn, iters)
+            except Exception as err:      # noqa: BLE001
+                out[key.replace("_ms", "_error")] = f"{type(err).__name__}: {err}"[:160]
+        return out
+
     # ------------------------------------------------------------------ flat all_reduce sweep
     sizes = [4096 << k for k in range(0, 19)]
     sizes = [s for s in sizes if s <= args.max_mb << 20]
@@ -109,6 +141,7 @@ def main():
             if not args.no_nccl:
                 nccl = timeit(lambda: dist.all_reduce(x), iters)
                 row.update(nccl_ms=nccl, nccl_bus_gbs=bus(nbytes, nccl))
+                row.update(symm_times(nbytes, dtype, iters))
             emit(**row)
             del x
 
@@ -133,7 +166,7 @@ def main():
     variants = [v for v in args.variants.split(";") if v] if args.variants else [""]
     for variant in variants:
         saved = {}
-        for kv in [x for x in variant.split(",") if x]:
+        for kv in [x for x in variant.split(",") if x and x != "default"]:
             k, v = kv.split("=", 1)
             saved[k] = os.environ.get(k)
             os.environ[k] = v

@@ -41,9 +41,14 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 
 __device__ __forceinline__ FxPad* pad_of(char* arena) { return reinterpret_cast<FxPad*>(arena); }
 
-// All CTAs `b` of the W ranks meet here.  `target` is the new epoch value.
-__device__ __forceinline__ void block_barrier(const FxLaunch& a, int rank, int world, int b,
+// All CTAs `b` of the W ranks meet here.  `target` is the new epoch value.  Returns false when a
+// peer did not arrive within the time bound: the sticky status word is set and the caller must
+// leave the kernel WITHOUT touching any output tensor (whatever sits in the peers' arenas is not
+// the data of this collective; the host raises at its next call / poll).
+__device__ __forceinline__ bool block_barrier(const FxLaunch& a, int rank, int world, int b,
                                               uint32_t target) {
+    __shared__ int s_timed_out;
+    if (threadIdx.x == 0) s_timed_out = 0;
     __syncthreads();
     if (threadIdx.x < world) {
         const int q = threadIdx.x;
@@ -61,12 +66,14 @@ __device__ __forceinline__ void block_barrier(const FxLaunch& a, int rank, int w
                 else if (now - t0 > a.timeout_ns) {        // peer never arrived: flag it, do not hang
                     *reinterpret_cast<volatile uint32_t*>(a.status) = (uint32_t)(-FX_ERR_TIMEOUT);
                     __threadfence_system();
+                    s_timed_out = 1;
                     break;
                 }
             }
         }
     }
     __syncthreads();
+    return s_timed_out == 0;
 }
 
 // ============================================================================ type traits
@@ -522,7 +529,8 @@ __device__ __forceinline__ void signal_peers(const FxLaunch& a, int which, int q
     st_release_sys(pipe_flag(a.arena[q], which, b, rank), value);
 }
 
-__device__ __forceinline__ void wait_peer(const FxLaunch& a, int which, int q, int rank, int b, uint32_t value) {
+// false: the peer never arrived (status word set); the caller must stop without writing outputs.
+__device__ __forceinline__ bool wait_peer(const FxLaunch& a, int which, int q, int rank, int b, uint32_t value) {
     const uint32_t* mine = pipe_flag(a.arena[rank], which, b, q);
     unsigned long long t0 = 0;
     uint32_t spins = 0;
@@ -533,10 +541,11 @@ __device__ __forceinline__ void wait_peer(const FxLaunch& a, int which, int q, i
             else if (now - t0 > a.timeout_ns) {
                 *reinterpret_cast<volatile uint32_t*>(a.status) = (uint32_t)(-FX_ERR_TIMEOUT);
                 __threadfence_system();
-                break;
+                return false;
             }
         }
     }
+    return true;
 }
 
 

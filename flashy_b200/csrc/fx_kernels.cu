@@ -50,14 +50,14 @@ __global__ void __launch_bounds__(FX_THREADS, 1) k_two_shot(const FxLaunch a) {
     const Meta m = load_meta(a, l, &meta_smem);
 
     move_all_slices<T, S, true>(m, stage, shard, slice, b, world);
-    block_barrier(a, rank, world, b, ++epoch);
+    if (!block_barrier(a, rank, world, b, ++epoch)) return;
 
     {
         const long long lo = rank * shard + b * slice;
         reduce_vectors<T, W, OP>(a, world, region + (unsigned long long)lo * sizeof(T),
                                  slice / (FX_VEC_BYTES / (long long)sizeof(T)), avg, my, block_lane());
     }
-    block_barrier(a, rank, world, b, ++epoch);
+    if (!block_barrier(a, rank, world, b, ++epoch)) return;
 
     {
         int first, step;
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(FX_THREADS, 1) k_one_shot(const FxLaunch a) {
     __shared__ MetaSmem meta_smem;
     const Meta m = load_meta(a, l, &meta_smem);
     move_slice<T, S, true>(m, reinterpret_cast<T*>(my + region), lo, hi, block_lane());
-    block_barrier(a, rank, world, b, ++epoch);
+    if (!block_barrier(a, rank, world, b, ++epoch)) return;
     reduce_unpack_range<T, S, OP>(a, m, world, region, lo, hi, a.op == FX_AVG);
     finish_launch(st, pad_of(my), b, epoch, calls);
 }
@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(FX_THREADS, 1) k_broadcast(const FxLaunch a) {
     __shared__ MetaSmem meta_smem;
     const Meta m = load_meta(a, l, &meta_smem);
     if (rank == a.src) move_all_slices<uint8_t, uint8_t, true>(m, reinterpret_cast<uint8_t*>(my + region), shard, slice, b, world);
-    block_barrier(a, rank, world, b, ++epoch);
+    if (!block_barrier(a, rank, world, b, ++epoch)) return;
     if (rank != a.src) {
         uint8_t* from = reinterpret_cast<uint8_t*>(a.arena[a.src] + region);
         int first, step;
@@ -153,13 +153,13 @@ __global__ void __launch_bounds__(FX_THREADS, 1) k_nvls(const FxLaunch a) {
     const Meta m = load_meta(a, l, &meta_smem);
 
     move_all_slices<T, S, true>(m, stage, shard, slice, b, world);
-    block_barrier(a, rank, world, b, ++epoch);
+    if (!block_barrier(a, rank, world, b, ++epoch)) return;
     {
         const long long lo = rank * shard + b * slice;
         nvls_vectors<T>(a.mc_arena + region + (unsigned long long)lo * sizeof(T),
                         slice / (FX_VEC_BYTES / (long long)sizeof(T)), avg, world, block_lane());
     }
-    block_barrier(a, rank, world, b, ++epoch);
+    if (!block_barrier(a, rank, world, b, ++epoch)) return;
     if (a.mode == FX_MODE_FUSED) move_all_slices<T, S, false>(m, stage, shard, slice, b, world);
     finish_launch(st, pad_of(my), b, epoch, calls);
 }
@@ -196,6 +196,8 @@ __global__ void __launch_bounds__(FX_THREADS, 1) k_pipe(const FxLaunch a) {
     const bool avg = a.op == FX_AVG;
     constexpr long long VEC = FX_VEC_BYTES / (long long)sizeof(T);
     __shared__ MetaSmem meta_smem;
+    __shared__ int s_abort;                 // a peer never arrived: every role stops before its next store
+    if (threadIdx.x == 0) s_abort = 0;
     const Meta m = load_meta(a, l, &meta_smem);
 
     const int warp = threadIdx.x >> 5;
@@ -219,8 +221,9 @@ __global__ void __launch_bounds__(FX_THREADS, 1) k_pipe(const FxLaunch a) {
         const Lane ln{rt, FX_RED_WARPS * 32};
         for (int c = 0; c < chunks; ++c) {
             const long long c0 = c * csz, c1 = (c0 + csz < slice) ? c0 + csz : slice;
-            if (rt < world) wait_peer(a, FX_FLAG_PACK, rt, rank, b, base + c + 1);
+            if (rt < world && !wait_peer(a, FX_FLAG_PACK, rt, rank, b, base + c + 1)) *reinterpret_cast<volatile int*>(&s_abort) = 1;
             named_sync(2, FX_RED_WARPS * 32);
+            if (*reinterpret_cast<volatile int*>(&s_abort)) break;
             const long long lo = rank * shard + b * slice + c0;
             const unsigned long long byte_off = region + (unsigned long long)lo * sizeof(T);
             if (NVLS) nvls_vectors<T>(a.mc_arena + byte_off, (c1 - c0) / VEC, avg, world, ln);
@@ -236,8 +239,9 @@ __global__ void __launch_bounds__(FX_THREADS, 1) k_pipe(const FxLaunch a) {
         const Lane ln = role_slice_lane(world, rw, FX_UNP_WARPS, &first, &step);
         for (int c = 0; c < chunks; ++c) {
             const long long c0 = c * csz, c1 = (c0 + csz < slice) ? c0 + csz : slice;
-            if (rt < world) wait_peer(a, FX_FLAG_RED, rt, rank, b, base + c + 1);
+            if (rt < world && !wait_peer(a, FX_FLAG_RED, rt, rank, b, base + c + 1)) *reinterpret_cast<volatile int*>(&s_abort) = 1;
             named_sync(3, FX_UNP_WARPS * 32);
+            if (*reinterpret_cast<volatile int*>(&s_abort)) break;
             for (int j = first; j < world; j += step) {
                 const int s = (rank + j) % world;
                 const long long lo = s * shard + b * slice;
@@ -261,7 +265,7 @@ __global__ void __launch_bounds__(FX_THREADS, 1) k_barrier(const FxLaunch a) {
     const int rank = a.rank0 + blockIdx.y;
     FxPad* pad = pad_of(a.arena[rank]);
     uint32_t epoch = pad->block_epoch[0];
-    block_barrier(a, rank, a.world, 0, ++epoch);
+    if (!block_barrier(a, rank, a.world, 0, ++epoch)) return;
     if (threadIdx.x == 0) pad->block_epoch[0] = epoch;
 }
 

@@ -773,6 +773,7 @@ def _sync_model_overlapped(ctx, model, entry: "_ModelLists", sync_buffers: bool,
         _check_number_of_params(grads + extra, (0x6F766C70, total, len(st.buckets)))   # ints only: str hashes differ per process
         st.checked = True
     st.finish(extra)
+    engine.poll()                                  # a flag-wait timeout of an earlier launch surfaces here, not a step later
     if sync_buffers and not average_buffers:
         broadcast_tensors(entry.float_buffers)
     return True
@@ -957,6 +958,7 @@ def eager_sync_gradients(params: tp.Iterable[torch.Tensor]):
                         assert params[i].grad is not None
                     _reduce(ctx, [fired[i] for i in got], [params[i].grad.data for i in got], N.FX_AVG, lossy=True)
         fired.clear()
+        engine.poll()                                  # device-side timeouts of the side-stream launches raise here
 
 
 @contextmanager
