@@ -629,8 +629,8 @@ def overlap(model: torch.nn.Module, enabled: bool = True, bucket_mb: tp.Optional
     gradients are grouped in buckets of ``bucket_mb`` MiB (``FLASHY_B200_OVERLAP_BUCKET_MB``, 8) in
     the order backward produces them, and a bucket is averaged IN PLACE on the communicator's side
     stream the moment its last gradient has been accumulated, while backward continues.
-    ``sync_model`` then only sends the tail bucket (the first layers' gradients plus the float
-    buffers) and makes the current stream wait.  The same ``sync_model`` call sites keep working;
+    ``sync_model`` then only sends the tail bucket (the first registered parameters' gradients, at most
+    ``FLASHY_B200_OVERLAP_TAIL_KB`` = 512 KiB, plus the float buffers) and makes the current stream wait.  The same ``sync_model`` call sites keep working;
     with several backward passes per ``sync_model`` (gradient accumulation) every pass re-averages,
     which gives the same mean by linearity.  Only the one-rank-per-process layout overlaps; the
     setting ``FLASHY_B200_OVERLAP=1`` enables it for every model passed to ``sync_model``."""
@@ -660,10 +660,21 @@ class _Overlap:
     def __init__(self, ctx, engine: Engine, entry: "_ModelLists", cap: int):
         self.ctx, self.engine = ctx, engine
         self.params = [p for p in entry.params if p.requires_grad]
-        # buckets in reverse registration order ~ the order backward yields gradients
+        # The tail bucket -- what sync_model itself has to send, i.e. the exposed part -- is the FIRST
+        # registered parameters (their gradients arrive last anyway), at most `tail` bytes; everything else
+        # is grouped in reverse registration order ~ the order backward yields gradients, `cap` bytes each.
+        tail = int(float(os.environ.get("FLASHY_B200_OVERLAP_TAIL_KB", "512")) * 1024)
+        n_tail, fill = 0, 0
+        for p in self.params:
+            size = p.numel() * p.element_size()
+            if n_tail and fill + size > tail:
+                break
+            if p.dtype != self.params[0].dtype:
+                break
+            n_tail, fill = n_tail + 1, fill + size
         self.buckets: tp.List[tp.List[int]] = []
         fill, last_dtype = 0, None
-        for i in range(len(self.params) - 1, -1, -1):
+        for i in range(len(self.params) - 1, n_tail - 1, -1):
             p = self.params[i]
             size = p.numel() * p.element_size()
             if self.buckets and p.dtype == last_dtype and fill + size <= cap:
@@ -672,6 +683,7 @@ class _Overlap:
             else:
                 self.buckets.append([i])
                 fill, last_dtype = size, p.dtype
+        self.buckets.append(list(range(n_tail - 1, -1, -1)))
         self.where = {}
         for k, idxs in enumerate(self.buckets):
             for i in idxs:
