@@ -30,7 +30,7 @@ KERNEL_NAMES = {1: "k_one_shot", 2: "k_two_shot", 3: "k_nvls", 4: "k_pipe<NVLS=f
 EXPORTS = (
     "fx_last_error", "fx_abi_version", "fx_cuda_available",
     "fx_comm_create", "fx_comm_export", "fx_comm_connect", "fx_comm_enable_multicast",
-    "fx_comm_get_info", "fx_comm_get_pointers", "fx_comm_trace_read", "fx_comm_poll", "fx_comm_abort", "fx_comm_destroy",
+    "fx_comm_get_info", "fx_comm_set_plan_blocks", "fx_comm_get_pointers", "fx_comm_trace_read", "fx_comm_poll", "fx_comm_abort", "fx_comm_destroy",
     "fx_host_exchange", "fx_host_barrier", "fx_host_broadcast",
     "fx_plan_create", "fx_plan_get_info", "fx_plan_offsets", "fx_plan_destroy",
     "fx_allreduce", "fx_broadcast", "fx_allreduce_begin", "fx_allreduce_finish", "fx_barrier",
@@ -79,6 +79,7 @@ def _load() -> C.CDLL:
         "fx_comm_connect": (i, [vp, vp, sz, i]),
         "fx_comm_enable_multicast": (i, [vp, vp, sz, i]),
         "fx_comm_get_info": (i, [vp, P(CommInfo)]),
+        "fx_comm_set_plan_blocks": (i, [vp, i]),
         "fx_comm_get_pointers": (i, [vp, P(vp), P(vp), P(u64), P(u64)]),
         "fx_comm_trace_read": (i, [vp, P(u64), sz, P(sz)]),
         "fx_comm_poll": (i, [vp]),

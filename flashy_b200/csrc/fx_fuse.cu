@@ -20,9 +20,9 @@
 //                     scope and writes "chunks < n of shard me are reduced" to every peer
 //   unpack  (1 warp)  arena (own after NVLS, peers' otherwise) -> shared memory -> output tensors
 //
-// Four reduce warps x 2 vectors per lane keep 4 KiB of multimem requests in flight per SM: the
-// measured plateau (2 KiB per SM already gives 837 of 841 GB/s bus; 64 KiB per SM drops to 770 and
-// only adds queueing in front of the flags -- profiles/r02_nvls_probe_n8.jsonl).  The reduce warps never execute a system-scope fence (1.75 us each on this system,
+// Four reduce warps x U vectors per lane (U = 1 by default) keep 2 KiB of multimem requests in flight
+// per SM: already the measured plateau (837 of 841 GB/s bus; 64 KiB per SM drops to 770 and only adds
+// queueing in front of the flags -- profiles/r02_nvls_probe_n8.jsonl).  The reduce warps never execute a system-scope fence (1.75 us each on this system,
 // profiles/r02_nvls_probe_n8.jsonl) and never wait for their own stores: the NVLink stream of a
 // CTA only stalls when a peer is late.  Pieces whose tensor address is not 16-byte aligned and
 // the (< 16 byte) tails of odd-sized tensors go through ordinary loads / stores of the same warp.
@@ -483,10 +483,10 @@ template <typename T>
 int launch_fuse_t(fx_plan* plan, const FxLaunch& a, size_t smem, cudaStream_t s) {
     if (plan->algo == FX_ALGO_NVLS) {
         switch (plan->fuse_unroll) {               // FLASHY_B200_FUSE_DEPTH: multimem vectors in flight per lane
-            case 1: return launch_fuse(k_fuse<T, true, 0, 1>, plan, a, smem, s);
+            case 2: return launch_fuse(k_fuse<T, true, 0, 2>, plan, a, smem, s);
             case 4: return launch_fuse(k_fuse<T, true, 0, 4>, plan, a, smem, s);
             case 8: return launch_fuse(k_fuse<T, true, 0, 8>, plan, a, smem, s);
-            default: return launch_fuse(k_fuse<T, true, 0, 2>, plan, a, smem, s);
+            default: return launch_fuse(k_fuse<T, true, 0, 1>, plan, a, smem, s);
         }
     }
     switch (a.world) {

@@ -668,6 +668,14 @@ extern "C" int fx_comm_get_info(fx_comm* c, fx_comm_info* info) {
     return FX_OK;
 }
 
+extern "C" int fx_comm_set_plan_blocks(fx_comm* c, int max_blocks) {
+    if (!c) return fx_fail(FX_ERR_INVALID, "comm is NULL");
+    if (max_blocks < 0) return fx_fail(FX_ERR_INVALID, "max_blocks must be >= 0");
+    std::lock_guard<std::mutex> lock(c->mu);
+    c->plan_blocks = max_blocks;
+    return FX_OK;
+}
+
 extern "C" int fx_comm_get_pointers(fx_comm* c, void** arenas, void** mc_base, uint64_t* mc_bytes, uint64_t* pad_bytes) {
     if (!c) return fx_fail(FX_ERR_INVALID, "comm is NULL");
     if (c->host_only || !c->connected) return fx_fail(FX_ERR_STATE, "needs a connected device communicator");
@@ -890,7 +898,8 @@ extern "C" int fx_plan_create(fx_comm* c, int world, const int64_t* numels, int 
     const int shards = (algo == FX_ALGO_ONE_SHOT) ? 1 : world;
     const long long slice_align = FX_SLICE_ALIGN / (long long)wsize;
     const size_t slice_target = (size_t)env_ll("FLASHY_B200_SLICE_BYTES", 8 << 10);
-    const int max_blocks = c && !c->host_only ? c->max_blocks : 148;
+    int max_blocks = c && !c->host_only ? c->max_blocks : 148;
+    if (c && c->plan_blocks > 0 && c->plan_blocks < max_blocks) max_blocks = c->plan_blocks;
     const long long per_shard = std::max<long long>((cur + shards - 1) / shards, 1);
     long long grid = (long long)(((size_t)per_shard * wsize + slice_target - 1) / slice_target);
     grid = std::max<long long>(1, std::min<long long>(grid, max_blocks));
@@ -929,8 +938,10 @@ extern "C" int fx_plan_create(fx_comm* c, int world, const int64_t* numels, int 
         while (cbytes > FX_SLICE_ALIGN && fx_fuse_smem_bytes(world, cbytes) > (size_t)(192 << 10)) cbytes -= FX_SLICE_ALIGN;
         if (fx_fuse_smem_bytes(world, cbytes) <= (size_t)(192 << 10)) {
             p->fuse_chunk = cbytes / (long long)wsize;
-            const long long depth = env_ll("FLASHY_B200_FUSE_DEPTH", 2);
-            p->fuse_unroll = (depth == 1 || depth == 4 || depth == 8) ? (int)depth : 2;
+            // 1 vector per lane = 2 KiB of multimem requests in flight per SM: measured best at 8 GPUs (R50 fp32
+            // bucket: 279 us against 296 / 294 / 296 us for 2 / 4 / 8; profiles/r02_sync_n8_variants.jsonl)
+            const long long depth = env_ll("FLASHY_B200_FUSE_DEPTH", 1);
+            p->fuse_unroll = (depth == 2 || depth == 4 || depth == 8) ? (int)depth : 1;
             p->fuse_chunks = (int)((p->slice + p->fuse_chunk - 1) / p->fuse_chunk);
         }
     }

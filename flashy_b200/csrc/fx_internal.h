@@ -98,6 +98,7 @@ struct fx_comm {
     int mem_kind = 0;
     bool host_only = false, connected = false, multicast = false;
     int sm_count = 0, max_blocks = 0;
+    int plan_blocks = 0;              // fx_comm_set_plan_blocks: grid cap of the plans created next (0 = max_blocks)
     size_t arena_bytes = 0;           // staging bytes per rank
     size_t arena_total = 0;           // pad + staging (allocation size)
     size_t arena_used = 0;            // bump pointer inside the staging area
@@ -140,7 +141,7 @@ struct fx_plan {
     long long chunk = 0;
     int fuse_chunks = 0;                        // fused TMA kernel (fx_fuse.cu): chunks per slice (0 = not eligible)
     long long fuse_chunk = 0;                   // elements per chunk of one sub-range
-    int fuse_unroll = 2;                        // NVLS: 16-byte multimem requests per lane in flight (1, 2, 4, 8)
+    int fuse_unroll = 1;                        // NVLS: 16-byte multimem requests per lane in flight (1, 2, 4, 8)
     size_t esize = 0, wsize = 0, wire_bytes = 0;
     size_t region[2] = {0, 0};
     bool recycled = false;                      // region memory was used by an earlier plan

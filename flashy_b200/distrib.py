@@ -630,7 +630,9 @@ def overlap(model: torch.nn.Module, enabled: bool = True, bucket_mb: tp.Optional
     the order backward produces them, and a bucket is averaged IN PLACE on the communicator's side
     stream the moment its last gradient has been accumulated, while backward continues.
     ``sync_model`` then only sends the tail bucket (the first registered parameters' gradients, at most
-    ``FLASHY_B200_OVERLAP_TAIL_KB`` = 512 KiB, plus the float buffers) and makes the current stream wait.  The same ``sync_model`` call sites keep working;
+    ``FLASHY_B200_OVERLAP_TAIL_KB`` = 512 KiB, plus the float buffers) and makes the current stream wait.
+    The buckets sent during backward use ``FLASHY_B200_OVERLAP_BLOCKS`` (32) CTAs instead of one per SM, so
+    that the compute kernels keep the other SMs.  The same ``sync_model`` call sites keep working;
     with several backward passes per ``sync_model`` (gradient accumulation) every pass re-averages,
     which gives the same mean by linearity.  Only the one-rank-per-process layout overlaps; the
     setting ``FLASHY_B200_OVERLAP=1`` enables it for every model passed to ``sync_model``."""
@@ -695,6 +697,7 @@ class _Overlap:
         self.pending = False                           # something is in flight on the side stream
         self.checked = False
         self.launched = 0                              # hook launches since the last sync_model
+        self.blocks = int(os.environ.get("FLASHY_B200_OVERLAP_BLOCKS", "32"))
         self.handles = [p.register_post_accumulate_grad_hook(lambda _p, i=i: self._on_grad(i))
                         for i, p in enumerate(self.params)]
 
@@ -726,7 +729,17 @@ class _Overlap:
         if cached is None or (ptrs != cached[1].last_in and _list_key(tensors) != cached[0]) \
                 or any(b.plan.handle is None for b in cached[1].buckets):
             key = _list_key(tensors)
-            layout = _layout_for(self.ctx, engine, "ar", tensors, N.FX_AVG, key, lossy=True)
+            # buckets launched DURING backward run on a small grid (FLASHY_B200_OVERLAP_BLOCKS, 32): every CTA of
+            # the fused kernel takes a whole SM's shared memory, and 148 of them would lock backward out.  What
+            # sync_model itself sends (tail, held-back buckets) is exposed anyway and uses the full grid.
+            engine.plan_blocks = self.blocks if tag[0] == "hook" else 0
+            try:
+                for _ in range(2):                             # an arena eviction while building: redo once
+                    layout = _build_layout(engine, "ar", tensors, N.FX_AVG, lossy=True)
+                    if all(b.plan.handle is not None for b in layout.buckets):
+                        break
+            finally:
+                engine.plan_blocks = 0
             self.layouts[tag] = cached = (key, layout)
         layout = cached[1]
         if ptrs != layout.last_in:

@@ -94,6 +94,7 @@ class Engine:
         self.side_stream = None if self.host_only else torch.cuda.Stream(device=self.device)
         self.layouts: tp.Dict[tp.Any, tp.Any] = {}       # bucket layouts of tensor lists (distrib.py)
         self.fast_lists: tp.Dict[tp.Any, tp.Any] = {}    # validated repeat lists of average_tensors (distrib.py)
+        self.plan_blocks = 0                             # > 0: grid cap for the plans created next (overlap buckets)
         self.multicast = bool(self.info.multicast)
         self.nvls_min = _env_int("FLASHY_B200_NVLS_MIN", 512 << 10)
         self.profile = False
@@ -173,14 +174,18 @@ class Engine:
     def get_plan(self, kind: str, numels: tp.Tuple[int, ...], dtype: int, wire: int, algo: int = N.FX_ALGO_AUTO,
                  tag: tp.Any = None) -> Plan:
         """Cached plan of one bucket.  ``tag`` distinguishes plans of identical shape that must not
-        share staging memory (several begin/finish buckets in flight at once)."""
+        share staging memory (several begin/finish buckets in flight at once).  ``self.plan_blocks``
+        (set around the call by the overlap code) caps the grid of newly created plans."""
         if self.host_only:
             raise RuntimeError("flashy_b200: no CUDA device in this process; tensor collectives have no CPU fallback")
+        if self.plan_blocks:
+            tag = (tag, "blocks", self.plan_blocks)
         key = (kind, numels, dtype, wire, algo) if tag is None else (kind, numels, dtype, wire, algo, tag)
         with self.lock:
             plan = self.plans.get(key)
             if plan is not None:
                 return plan
+            N.check(N.lib.fx_comm_set_plan_blocks(self.comm, int(self.plan_blocks)))
             try:
                 plan = Plan(self, key, numels, dtype, wire, algo)
             except N.NativeError as err:

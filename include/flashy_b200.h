@@ -138,6 +138,12 @@ int fx_comm_connect(fx_comm* comm, const void* blobs, size_t blob_len, int n_pro
  * device, driver or allocation kind cannot do it; the P2P algorithms keep working. */
 int fx_comm_enable_multicast(fx_comm* comm, const void* blobs, size_t blob_len, int n_procs);
 int fx_comm_get_info(fx_comm* comm, fx_comm_info* info);
+/* Cap gridDim.x of the plans created AFTER this call (0 = back to the communicator's default, one CTA per
+ * SM).  Every rank must make the same calls in the same order (the grid is part of the bucket layout).
+ * Used for the buckets that are launched while backward is still running: a small grid leaves the other
+ * SMs -- each CTA of the fused kernel takes a whole SM's shared memory -- to the compute kernels.
+ * No reference counterpart (NCCL's channel count plays this role in the reference). */
+int fx_comm_set_plan_blocks(fx_comm* comm, int max_blocks);
 /* Diagnostics / benchmarks: the arena base of every rank as mapped in this process
  * (`arenas[world]`, staging starts `pad_bytes` in), and the NVSwitch multicast alias of the
  * arenas (`mc_base` NULL / `mc_bytes` 0 without NVLS).  No reference counterpart: this is
