@@ -16,11 +16,11 @@ virtual ranks of one process (one thread + one CUDA stream each); every ``sync_m
 ``value`` times K steps with the batch resident in HBM; ``e2e`` times K more steps through the
 same public API with the batch copied from pinned host memory and the loss read back each step.
 
-With one rank per GPU (N = 8) the step is captured as ONE CUDA graph of forward, backward and
+``--overlap`` (one rank per GPU only) captures the step as ONE CUDA graph of forward, backward and
 ``sync_model`` with backward overlap enabled (``distrib.overlap(model)``: gradient buckets leave on
 the communicator's side stream while backward still runs; ``sync_model`` sends the tail bucket and
-joins); ``--no-overlap`` gives the round-1 step (graph of forward+backward, then one exposed
-``sync_model`` launch).  Before anything is timed, at every N, the real 62-tensor bf16 gradient
+joins).  It is off by default: on this latency-bound batch-64 step it measured slower than one exposed
+``sync_model`` launch (profiles/README.md).  Before anything is timed, at every N, the real 62-tensor bf16 gradient
 bucket is averaged once with seeded inputs and compared with ``oracle/numeric.py`` (checker use
 only, outside every timed region): the ``parity`` object, and a non-zero exit on mismatch.
 ``--model resnet50 --image 224 --batch 32`` is BASELINE configs[2].
@@ -58,7 +58,9 @@ def parse():
     ap.add_argument("--kernel-table", default="", help="write a per-kernel device-time table of the timed region (CUPTI) to this file")
     ap.add_argument("--model", default="resnet18", choices=("resnet18", "resnet50"))
     ap.add_argument("--image", type=int, default=32, help="square image size (32: CIFAR, 224: ImageNet-shaped)")
-    ap.add_argument("--no-overlap", action="store_true", help="one exposed sync_model launch after backward (round-1 step)")
+    ap.add_argument("--overlap", action="store_true",
+                    help="capture the step with distrib.overlap(model): gradient buckets leave during backward (measured slower "
+                         "for this latency-bound step, see profiles/README.md; default: one sync_model launch after backward)")
     ap.add_argument("--no-parity", action="store_true", help="skip the pre-timing parity check against the oracle")
     return ap.parse_args()
 
@@ -270,7 +272,7 @@ def native_arm(args) -> None:
     if proc_world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("gloo", init_method="env://")        # bootstrap + timing reduction only
-    overlap = n_local == 1 and W > 1 and not args.no_overlap and not args.no_graphs
+    overlap = n_local == 1 and W > 1 and args.overlap and not args.no_graphs
 
     vw = VirtualWorld(n_local, device=local_rank) if n_local > 1 else None
 

@@ -244,6 +244,8 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) k_fuse(const FxLaunch a) {
             next = covered;
             // order the flag behind the reduce warps' stores (cumulative): they went to every peer's arena with
             // NVLS (system scope), to this GPU's own arena otherwise (GPU scope is enough, see signal_packed)
+            // (holding the reduce warps' stores back for the moment of the fence was tried: fences stay 3-6 us at two
+            //  GPUs either way and the kernel gets 7-9 % slower -- profiles/r02_raw/sync_n2_pause.jsonl)
             if (NVLS) fence_sys(); else fence_gpu();
             if (trace && lane == 0) trace[FZ_TR_SIG + 2 * (next - 1) + 1] = globaltimer_ns();
             if (lane < world) st_relaxed_sys(pipe_flag(a.arena[lane], FX_FLAG_RED, b, rank), base + (uint32_t)next);
@@ -483,10 +485,10 @@ template <typename T>
 int launch_fuse_t(fx_plan* plan, const FxLaunch& a, size_t smem, cudaStream_t s) {
     if (plan->algo == FX_ALGO_NVLS) {
         switch (plan->fuse_unroll) {               // FLASHY_B200_FUSE_DEPTH: multimem vectors in flight per lane
-            case 2: return launch_fuse(k_fuse<T, true, 0, 2>, plan, a, smem, s);
+            case 1: return launch_fuse(k_fuse<T, true, 0, 1>, plan, a, smem, s);
             case 4: return launch_fuse(k_fuse<T, true, 0, 4>, plan, a, smem, s);
             case 8: return launch_fuse(k_fuse<T, true, 0, 8>, plan, a, smem, s);
-            default: return launch_fuse(k_fuse<T, true, 0, 1>, plan, a, smem, s);
+            default: return launch_fuse(k_fuse<T, true, 0, 2>, plan, a, smem, s);
         }
     }
     switch (a.world) {

@@ -938,10 +938,13 @@ extern "C" int fx_plan_create(fx_comm* c, int world, const int64_t* numels, int 
         while (cbytes > FX_SLICE_ALIGN && fx_fuse_smem_bytes(world, cbytes) > (size_t)(192 << 10)) cbytes -= FX_SLICE_ALIGN;
         if (fx_fuse_smem_bytes(world, cbytes) <= (size_t)(192 << 10)) {
             p->fuse_chunk = cbytes / (long long)wsize;
-            // 1 vector per lane = 2 KiB of multimem requests in flight per SM: measured best at 8 GPUs (R50 fp32
-            // bucket: 279 us against 296 / 294 / 296 us for 2 / 4 / 8; profiles/r02_sync_n8_variants.jsonl)
-            const long long depth = env_ll("FLASHY_B200_FUSE_DEPTH", 1);
-            p->fuse_unroll = (depth == 2 || depth == 4 || depth == 8) ? (int)depth : 1;
+            // Multimem vectors in flight per lane.  A rank reduces N / W bytes, so the depth the links need shrinks
+            // with the world: 1 (2 KiB per SM) is best at 8 GPUs (ResNet-50 fp32 bucket 279 us against 296 / 294 / 296
+            // for 2 / 4 / 8, profiles/r02_sync_n8_variants.jsonl), at 2 GPUs 1 loses a third against 8
+            // (546 vs 365 us, profiles/r02_raw/).
+            const long long auto_depth = world >= 8 ? 1 : (world >= 4 ? 2 : 4);
+            const long long depth = env_ll("FLASHY_B200_FUSE_DEPTH", auto_depth);
+            p->fuse_unroll = (depth == 1 || depth == 2 || depth == 4 || depth == 8) ? (int)depth : (int)auto_depth;
             p->fuse_chunks = (int)((p->slice + p->fuse_chunk - 1) / p->fuse_chunk);
         }
     }
