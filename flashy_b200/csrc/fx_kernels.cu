@@ -404,11 +404,9 @@ int fx_max_coresident_blocks(int device, int n_local, int* sm_count) {
     int sms = 0;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return 0;
     if (sm_count) *sm_count = sms;
-    int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_two_shot<float, float, 8, FX_SUM>, FX_THREADS, 0) != cudaSuccess || occ < 1)
-        occ = 1;
-    occ = 1;                                           // every kernel is built for one CTA per SM
-    int blocks = sms * occ / (n_local > 0 ? n_local : 1);
+    // Every collective kernel is built for ONE CTA per SM (__launch_bounds__(.., 1); k_fuse takes the whole
+    // shared memory of its SM), and the hosted ranks' CTAs must all be resident at once.
+    int blocks = sms / (n_local > 0 ? n_local : 1);
     if (blocks > FX_MAX_BLOCKS) blocks = FX_MAX_BLOCKS;
     return blocks < 1 ? 1 : blocks;
 }

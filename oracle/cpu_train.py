@@ -56,15 +56,21 @@ def partition_cores(cores, world):
     return [cores[r * k:(r + 1) * k] for r in range(world)]
 
 
-def _worker(rank: int, world: int, port: int, batch: int, steps: int, warmup: int, cores, queue):
+def _worker(rank: int, world: int, port: int, batch: int, steps: int, warmup: int, cores, queue, spare: int = 0,
+            passive: bool = False):
     scrub_launcher_env()
     if cores:
         try:
             os.sched_setaffinity(0, cores)
         except OSError:
             pass
-    threads = max(1, len(cores)) if cores else 1
+    # `spare` cores of the rank's set are left to gloo's own threads; `passive` makes idle OpenMP workers sleep
+    # instead of spinning on the cores the transport needs
+    threads = max(1, len(cores) - spare) if cores else 1
     os.environ["OMP_NUM_THREADS"] = str(threads)
+    if passive:
+        os.environ["OMP_WAIT_POLICY"] = "passive"
+        os.environ["GOMP_SPINCOUNT"] = "0"
     if str(ROOT) not in sys.path:
         sys.path.insert(0, str(ROOT))
     import torch
@@ -106,7 +112,7 @@ def _worker(rank: int, world: int, port: int, batch: int, steps: int, warmup: in
 
 
 def run(world: int = 8, batch: int = 8, steps: int = 5, warmup: int = 1, cores: int | None = None,
-        timeout_s: float = 780.0) -> dict:
+        timeout_s: float = 780.0, pin: bool = True, spare: int = 0, passive: bool = False) -> dict:
     """Returns samples/s of the whole W-rank CPU job plus how it was obtained."""
     try:
         avail = sorted(os.sched_getaffinity(0))
@@ -115,11 +121,16 @@ def run(world: int = 8, batch: int = 8, steps: int = 5, warmup: int = 1, cores: 
     if cores:
         avail = avail[:cores]
     sets = partition_cores(avail, world)
-    threads = max(1, len(sets[0]))
+    threads = max(1, len(sets[0]) - spare)
+    k = len(sets[0])
+    if not pin:                                   # same thread count, placement left to the OS scheduler
+        sets = [[] for _ in range(world)]
+        threads = max(1, k - spare)
     ctx = mp.get_context("spawn")
     queue = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, batch, steps, warmup, sets[r], queue))
+    procs = [ctx.Process(target=_worker, args=(r, world, port, batch, steps, warmup, sets[r] if pin else list(avail), queue,
+                                               (len(avail) - threads) if not pin else spare, passive))
              for r in range(world)]
     t0 = time.perf_counter()
     for p in procs:
