@@ -332,6 +332,31 @@ __global__ void k_latency(const ProbeArgs a) {
         t1 = gtimer();
         a.out[9] = (t1 - t0) / a.iters;
     }
+    // 10: cp.async.bulk of a 4 KiB shared-memory tile to the MULTICAST address + wait_group 0 (completion of the
+    //     bulk group instead of an SM-wide system fence); 11: the same to the own (unicast) arena
+    {
+        __shared__ __align__(128) unsigned char tile[4096];
+        for (int i = 0; i < 4096; i += 4) *reinterpret_cast<uint32_t*>(tile + i) = 0x5a000000u + (uint32_t)a.rank;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (a.mc) {
+            t0 = gtimer();
+            for (int i = 0; i < a.iters; ++i) {
+                tma_store(a.mc + off + (size_t)(a.rank * a.iters + i) * 4096, tile, 4096);
+                tma_commit();
+                tma_wait_all();
+            }
+            t1 = gtimer();
+            a.out[10] = (t1 - t0) / a.iters;
+        }
+        t0 = gtimer();
+        for (int i = 0; i < a.iters; ++i) {
+            tma_store(a.arena[a.rank] + off + (size_t)(a.world * a.iters + i) * 4096, tile, 4096);
+            tma_commit();
+            tma_wait_all();
+        }
+        t1 = gtimer();
+        a.out[11] = (t1 - t0) / a.iters;
+    }
     a.out[15] = acc;
 }
 

@@ -208,6 +208,16 @@ def main():
         torch.cuda.synchronize()
         lat = out.cpu().tolist()
         dist.barrier()
+        if have_mc:
+            shard = nbytes // world
+            ok = True
+            for r in range(world):                     # rank r stored 64 tiles at ITS shard offset of every arena
+                tiles = torch.empty(64 * 4096, dtype=torch.uint8, device=dev)
+                memcpy(tiles.data_ptr(), arenas[rank] + region + r * shard + r * 64 * 4096, tiles.numel())
+                ok = ok and bool((tiles.view(torch.int32) == 0x5a000000 + r).all())
+            flag = torch.tensor([1.0 if ok else 0.0], dtype=torch.float64)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            emit(kind="sanity", what="cp.async.bulk store to the multicast address lands in every rank's arena", ok=bool(flag[0] == 1.0))
         bar = {}
         epochs = {0: 0, 1: 0, 2: 0}
         epochs[3] = 0
@@ -235,10 +245,11 @@ def main():
             row["copy_gbs_rw"] = 2 * (2 * nbytes) / (ms * 1e-3) / 1e9
         emit(**row)
     if lat is not None:
-        lt = torch.tensor(lat[:10], dtype=torch.float64)
+        lt = torch.tensor(lat[:12], dtype=torch.float64)
         dist.all_reduce(lt, op=dist.ReduceOp.MAX)
         names = ["local_ld_ns", "peer_ld_ns", "multimem_ld_reduce_ns", "multimem_st_fence_ns", "peer_st_fence_ns",
-                 "local_st_fence_ns", "fence_ns", "fence_gpu_ns", "local_st_fence_gpu_ns", "multimem_st_fence_gpu_ns"]
+                 "local_st_fence_ns", "fence_ns", "fence_gpu_ns", "local_st_fence_gpu_ns", "multimem_st_fence_gpu_ns",
+                 "bulk_store_4k_to_multicast_wait_ns", "bulk_store_4k_local_wait_ns"]
         emit(kind="latency", **{n: v for n, v in zip(names, lt.tolist())})
         for variant, vals in bar.items():
             bt = torch.tensor(vals, dtype=torch.float64)

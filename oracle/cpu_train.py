@@ -7,11 +7,16 @@ reference's own call sequence as restated in ``oracle/refdistrib.py`` (one all-r
 divide per tensor, two host-synchronising count checks).  Used by ``bench.py`` for the
 ``cpu_baseline`` object and for ``--impl reference``.
 
-Stability measures (the same code moved 4.6x between two boxes in round 1): every rank is pinned
-to its own disjoint set of cores (``os.sched_setaffinity``) with one OpenMP thread per core, the
-reported step time is the MEDIAN over the timed steps of the per-step max over ranks, and the
-rendezvous is an explicit ``tcp://`` store so that a surrounding ``torch.distributed.run`` agent
-(``TORCHELASTIC_*`` variables) cannot redirect it.
+Placement (measured on the GPU box's 128-core host, ``benchmarks/cpu_baseline_variants.py`` ->
+``profiles/r02_cpu_baseline_variants.jsonl``): with OpenMP's default ACTIVE wait policy the idle
+workers of 8 x 16 threads spin on the very cores gloo's transport threads need -- 160 samples/s
+pinned, 387 unpinned, and a 4.6x spread between two boxes in round 1.  With a PASSIVE wait policy
+(``OMP_WAIT_POLICY=passive``, ``GOMP_SPINCOUNT=0``) the same job runs at 1 430 - 1 450 samples/s.
+The default is therefore the fastest stable configuration found: every rank pinned to its own
+disjoint core set (``os.sched_setaffinity``), one core of the set left to the transport, passive
+waiting; the reported step time is the MEDIAN over the timed steps of the per-step max over ranks,
+and the rendezvous is an explicit ``tcp://`` store so that a surrounding ``torch.distributed.run``
+agent (``TORCHELASTIC_*`` variables) cannot redirect it.
 """
 from __future__ import annotations
 
@@ -112,7 +117,7 @@ def _worker(rank: int, world: int, port: int, batch: int, steps: int, warmup: in
 
 
 def run(world: int = 8, batch: int = 8, steps: int = 5, warmup: int = 1, cores: int | None = None,
-        timeout_s: float = 780.0, pin: bool = True, spare: int = 0, passive: bool = False) -> dict:
+        timeout_s: float = 780.0, pin: bool = True, spare: int = 1, passive: bool = True) -> dict:
     """Returns samples/s of the whole W-rank CPU job plus how it was obtained."""
     try:
         avail = sorted(os.sched_getaffinity(0))
@@ -121,8 +126,10 @@ def run(world: int = 8, batch: int = 8, steps: int = 5, warmup: int = 1, cores: 
     if cores:
         avail = avail[:cores]
     sets = partition_cores(avail, world)
-    threads = max(1, len(sets[0]) - spare)
     k = len(sets[0])
+    if k <= 1:
+        spare = 0                                 # a single core per rank: nothing to spare
+    threads = max(1, k - spare)
     if not pin:                                   # same thread count, placement left to the OS scheduler
         sets = [[] for _ in range(world)]
         threads = max(1, k - spare)
@@ -153,11 +160,12 @@ def run(world: int = 8, batch: int = 8, steps: int = 5, warmup: int = 1, cores: 
     return {
         "value": world * batch / med,
         "unit": "samples/s",
-        "cores": threads * world if sets[0] else min(len(avail), world),
+        "cores": min(len(avail), max(k, 1) * world),
         "kind": "port",
         "sample": (f"median of {steps} timed steps (+{warmup} warm-up) of the ResNet-18/CIFAR step, world {world} gloo "
-                   f"processes x batch {batch}, fp32 on CPU, {threads} pinned core(s) per rank "
-                   f"({'pinned' if sets[0] else 'unpinned'}); sync_model (oracle/refdistrib.py) median "
+                   f"processes x batch {batch}, fp32 on CPU, {threads} OpenMP thread(s) per rank on {max(k, 1)} "
+                   f"{'pinned' if pin and k else 'unpinned'} core(s), {'passive' if passive else 'active'} OpenMP waiting; "
+                   f"sync_model (oracle/refdistrib.py) median "
                    f"{1e3 * sync_med:.0f} ms/step; step min/max {1e3 * min(out['step_s']):.0f}/{1e3 * max(out['step_s']):.0f} ms; "
                    f"{wall:.0f} s wall including process start-up"),
         "ms_per_step": 1e3 * med,

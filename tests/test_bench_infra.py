@@ -41,6 +41,7 @@ def test_reference_arm_runs_under_a_launcher_environment():
     import json
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["value"] > 0 and "pinned" in line["cpu_baseline"]["sample"]
+    assert "passive" in line["cpu_baseline"]["sample"]
     assert line["config"]["world"] == 2 and "ranks_per_gpu" not in line["config"]       # same config object as the native arm
     # rank 1 of the launcher prints nothing and exits 0
     env["RANK"] = "1"
