@@ -1,3 +1,5 @@
+#!/bin/bash
+# Step time of bench.py with / without backward overlap at 2 GPUs (one rank per GPU): gpurun --gpus 2 -- bash benchmarks/overlap_variants.sh
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1"
 run() { tag=$1; shift; env "$@" timeout 150 $TR --master-port 29510 bench.py --gpus 2 --world 2 --steps 15 --warmup 3 --no-parity $EXTRA > gpurun_out/ovl_$tag.json 2> gpurun_out/ovl_$tag.err; python - <<PY
 import json
@@ -8,9 +10,9 @@ except Exception as e:
     print("$tag failed", e)
 PY
 }
-EXTRA="--no-overlap" run noovl A=1
-EXTRA="" run b32 FLASHY_B200_OVERLAP_BLOCKS=32
-EXTRA="" run b148 FLASHY_B200_OVERLAP_BLOCKS=148
-EXTRA="" run b16 FLASHY_B200_OVERLAP_BLOCKS=16
-EXTRA="" run b32_4mb FLASHY_B200_OVERLAP_BLOCKS=32 FLASHY_B200_OVERLAP_BUCKET_MB=4
-EXTRA="" run b32_nvls FLASHY_B200_OVERLAP_BLOCKS=32 FLASHY_B200_NVLS_MIN_WORLD=2
+EXTRA="" run noovl A=1
+EXTRA="--overlap" run b32 FLASHY_B200_OVERLAP_BLOCKS=32
+EXTRA="--overlap" run b148 FLASHY_B200_OVERLAP_BLOCKS=148
+EXTRA="--overlap" run b16 FLASHY_B200_OVERLAP_BLOCKS=16
+EXTRA="--overlap" run b32_4mb FLASHY_B200_OVERLAP_BLOCKS=32 FLASHY_B200_OVERLAP_BUCKET_MB=4
+EXTRA="--overlap" run b32_nvls FLASHY_B200_OVERLAP_BLOCKS=32 FLASHY_B200_NVLS_MIN_WORLD=2
