@@ -13,19 +13,20 @@
 //                     chunk, then "chunk c packed" to every peer's flags_pack[b][me]
 //   poll    (1 warp)  reads flags_pack[b][*] / flags_red[b][*] of the own pad and publishes the
 //                     minimum over ranks in shared memory (what every rank has packed / reduced)
-//   reduce  (4 warps) 1 KiB units of a chunk, round-robin over the warps: multimem.ld_reduce of the own
-//                     shard's sub-range through the NVSwitch, / W, multimem.st to all arenas
+//   reduce  (4 warps) units of 32 * U vectors of a chunk, round-robin over the warps: multimem.ld_reduce
+//                     of the own shard's sub-range through the NVSwitch, / W, multimem.st to all arenas
 //                     (or, without multicast: pull the W arenas in rank order, write the own one)
 //   signal  (1 warp)  watches the reduce warps' progress in shared memory, fences ONCE at system
 //                     scope and writes "chunks < n of shard me are reduced" to every peer
 //   unpack  (1 warp)  arena (own after NVLS, peers' otherwise) -> shared memory -> output tensors
 //
-// Four reduce warps x U vectors per lane (U = 1 by default) keep 2 KiB of multimem requests in flight
-// per SM: already the measured plateau (837 of 841 GB/s bus; 64 KiB per SM drops to 770 and only adds
-// queueing in front of the flags -- profiles/r02_nvls_probe_n8.jsonl).  The reduce warps never execute a system-scope fence (1.75 us each on this system,
-// profiles/r02_nvls_probe_n8.jsonl) and never wait for their own stores: the NVLink stream of a
-// CTA only stalls when a peer is late.  Pieces whose tensor address is not 16-byte aligned and
-// the (< 16 byte) tails of odd-sized tensors go through ordinary loads / stores of the same warp.
+// Four reduce warps x U vectors per lane (U = 1 at 8 GPUs) keep 2 KiB of multimem requests in flight per
+// SM: already the measured plateau (837 of 841 GB/s bus; 64 KiB per SM drops to 770 and only adds
+// queueing in front of the flags -- profiles/r02_nvls_probe_n8.jsonl).  The reduce warps never execute
+// a system-scope fence (1.76 us unloaded, 12-18 us while the SM streams multicast stores) and never wait
+// for their own stores: the NVLink stream of a CTA only stalls when a peer is late.  Pieces whose tensor
+// address is not 16-byte aligned and the (< 16 byte) tails of odd-sized tensors go through ordinary
+// loads / stores of the same warp.
 #include "fx_device.cuh"
 
 namespace {
@@ -119,7 +120,7 @@ struct FuseSync {
     uint64_t full_pack[FZ_NB], full_unp[FZ_NB];   // "the bulk loads of this buffer have landed"
     uint32_t packed;                       // chunks every rank has packed (this launch)
     uint32_t reduced;                      // chunks of every shard reduced and delivered
-    uint32_t red_prog[FZ_RED_WARPS];       // chunks completed by each reduce warp
+    uint32_t red_prog[FZ_RED_WARPS];       // units completed by each reduce warp
     uint32_t abort;                        // a peer never arrived: stop without touching the outputs
 };
 

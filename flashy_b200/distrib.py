@@ -14,8 +14,10 @@ data: CPU tensors in a distributed collective raise.
 Environment knobs (none of them changes a public signature):
 ``FLASHY_B200_ARENA_MB`` (1024), ``FLASHY_B200_BUCKET_MB`` (128), ``FLASHY_B200_EAGER_BUCKET_MB`` (8),
 ``FLASHY_B200_ONE_SHOT_MAX`` (bytes, 262144), ``FLASHY_B200_SLICE_BYTES`` (8192),
-``FLASHY_B200_WIRE=bf16`` (send fp32 gradients as bf16: opt-in, lossy),
-``FLASHY_B200_CHECK=always|plan`` (count check every call, or only when a bucket plan is new).
+``FLASHY_B200_WIRE=bf16`` (send fp32 gradients as bf16: opt-in, lossy, averaged gradients only),
+``FLASHY_B200_CHECK=always|plan`` (count check every call, or only when a bucket plan is new),
+``FLASHY_B200_OVERLAP=1`` / ``FLASHY_B200_OVERLAP_BUCKET_MB`` (8) / ``FLASHY_B200_OVERLAP_TAIL_KB`` (512) /
+``FLASHY_B200_OVERLAP_BLOCKS`` (32): backward overlap for ``sync_model`` (see ``overlap``; an addition, off by default).
 """
 from __future__ import annotations
 
