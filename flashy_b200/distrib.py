@@ -774,10 +774,14 @@ class _Overlap:
         if tail:
             self._launch(("tail", len(tail)), tail)
         if self.pending:
-            done = torch.cuda.Event()
-            done.record(self.engine.side_stream)
-            torch.cuda.current_stream().wait_event(done)
+            self._join()
             self.pending = False
+
+    def _join(self) -> None:
+        """The current stream waits for everything launched on the side stream."""
+        done = torch.cuda.Event()
+        done.record(self.engine.side_stream)
+        torch.cuda.current_stream().wait_event(done)
 
 
 def _sync_model_overlapped(ctx, model, entry: "_ModelLists", sync_buffers: bool, average_buffers: bool) -> bool:
