@@ -68,12 +68,10 @@ def test_sync_model_follows_a_replaced_head():
     ``model.fc`` between two ``sync_model`` calls: the NEW parameters' gradients must be averaged on the
     very next call."""
     from flashy_b200 import VirtualWorld, distrib
-    numeric = _oracle()
     world = 4
     vw = VirtualWorld(world, device=0, arena_mb=64)
     try:
         def body(rank, w):
-            torch.manual_seed(0)
             model = nn.Sequential(nn.Linear(64, 512), nn.ReLU(), nn.Linear(512, 300)).cuda()
             model.add_module("fc", nn.Linear(300, 10).cuda())
             for p in model.parameters():
@@ -96,7 +94,6 @@ def test_sync_model_follows_a_replaced_head():
         assert got[-1].shape == (7,) and got[-2].shape == (7, 300)
         for g in got:
             assert torch.equal(g, torch.full_like(g, want))
-    del numeric
 
 
 @pytest.mark.gpu
