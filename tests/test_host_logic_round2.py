@@ -100,3 +100,23 @@ def test_overlap_holds_back_buckets_with_a_missing_gradient():
         assert sent_params == len(ov.params) - 2                              # everything except the skipped layer
     finally:
         ov.remove()
+
+
+def test_signaller_coverage_formula_matches_a_brute_force_model():
+    """fx_fuse.cu, signal role: reduce warp w owns units w, w + R, ... of the chunk-major unit sequence and reports
+    how many it has finished; chunks are complete up to min_w floor((done_w * R + w) / units_per_chunk).  Checked
+    against an explicit simulation for every reachable progress state of small configurations."""
+    import itertools
+    R = 4
+    for chunks, upc in ((1, 1), (5, 1), (3, 2), (4, 4), (2, 8), (7, 3)):
+        units = chunks * upc
+        owned = [len(range(w, units, R)) for w in range(R)]
+        for done in itertools.product(*[range(n + 1) for n in owned]):
+            finished = set()
+            for w in range(R):
+                finished.update(list(range(w, units, R))[:done[w]])
+            brute = 0
+            while brute < chunks and all(u in finished for u in range(brute * upc, (brute + 1) * upc)):
+                brute += 1
+            formula = min(min((done[w] * R + w) // upc, chunks) for w in range(R))
+            assert formula == brute, (chunks, upc, done, formula, brute)
